@@ -1,0 +1,33 @@
+"""Stand-in for the few gym names the reference env adapters import (gym is not installed here).
+
+TEST INFRASTRUCTURE ONLY.  Semantics that matter for parity: spaces.Box casts low/high to its
+dtype (float32 for the single-agent env, which fixes the dtype of the normalisation arithmetic,
+reference gym_highway/envs/highway_env.py:51 and :131-140).
+"""
+from . import spaces, utils, error  # noqa: F401
+from . import envs  # noqa: F401
+
+
+class Env(object):
+    metadata = {}
+    reward_range = (-float("inf"), float("inf"))
+    spec = None
+    action_space = None
+    observation_space = None
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def close(self):
+        return None
+
+    def seed(self, seed=None):
+        return []
+
+
+class Wrapper(Env):
+    def __init__(self, env):
+        self.env = env
+        self.action_space = env.action_space
+        self.observation_space = env.observation_space
