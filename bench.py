@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the batched highway step path (contract: see the task brief / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--workload sa_discrete|sa_continuous|ma_discrete|ma_continuous]
+    python bench.py --impl reference ...     # the CPU arm: C restatement of the reference on all host cores
+
+One "step" = one env.step() of every environment of the batch (9 simulator ticks, collision tests,
+observation, reward, done, auto-reset) = ONE kernel launch.  Prints ONE JSON line on rank 0.
+
+Timing: CUDA events on the launching stream around every step launch; the L2 (126 MB) is flushed
+between timed launches by overwriting a 256 MiB buffer (outside the event pairs) unless the batch's
+working set is itself larger than L2 (--envs >= 2M), so every launch reads its state from HBM.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SA_BYTES_PER_STEP = {False: 273, True: 277}  # 96 B state in + 96 B out + action + 72 B obs + 4 B rew + 1 B done
+L2_BYTES = 126 * 1024 * 1024
+
+
+def ma_bytes_per_step(A, K):
+    return 2 * (36 * A + 16 * K + 32) + 4 * A + 4 * A * (4 * A + 14) + 4 * A + A
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--envs", type=int, default=65536, help="environments PER GPU (weak scaling)")
+    ap.add_argument("--workload", default="sa_discrete")
+    ap.add_argument("--agents", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=0, help="steps of the bounded CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_info(args):
+    w = args.workload
+    cont = w.endswith("continuous")
+    if w.startswith("sa_"):
+        return dict(kind="sa", continuous=cont, bytes_per_step=SA_BYTES_PER_STEP[cont],
+                    name="single-agent 3-lane env, %d envs/GPU, %s random actions" % (args.envs, "continuous" if cont else "discrete"),
+                    dtype="f64 tick arithmetic on f32 state")
+    return dict(kind="ma", continuous=cont, bytes_per_step=ma_bytes_per_step(args.agents, 16),
+                name="multi-agent highway env, %d cars x %d envs/GPU, %s random actions" % (args.agents, args.envs, "continuous" if cont else "discrete"),
+                dtype="f64 tick arithmetic on f32 state")
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_arm(args, info, steps_hint=0, nthreads=None):
+    """time the C restatement of the reference step on the host cores: bounded sample of the workload"""
+    from oracle import oracle as orc
+    nthreads = nthreads or os.cpu_count() or 1
+    n = min(args.envs, 65536)
+    rng = np.random.RandomState(1234)
+    if info["kind"] == "sa":
+        st = orc.SaState(n)
+        orc.sa_reset(st)
+
+        def one_step():
+            act = rng.uniform(-1, 1, (n, 2)).astype(np.float32) if info["continuous"] else rng.randint(0, 4, n).astype(np.int32)
+            t0 = time.perf_counter()
+            orc.sa_step(st, act, continuous=info["continuous"], seed=0, quantise=True, nthreads=nthreads)
+            return time.perf_counter() - t0
+    else:
+        from oracle import ma_oracle as mo
+        st = mo.MaState(n, args.agents)
+        mo.ma_reset(st)
+
+        def one_step():
+            A = args.agents
+            act = rng.uniform(-1, 1, (n, A, 2)).astype(np.float32) if info["continuous"] else rng.randint(0, 4, (n, A)).astype(np.int32)
+            t0 = time.perf_counter()
+            mo.ma_step(st, act, continuous=info["continuous"], seed=0, quantise=True, nthreads=nthreads)
+            return time.perf_counter() - t0
+    for _ in range(3):
+        one_step()
+    probe = one_step()
+    steps = steps_hint or int(max(10, min(2000, 12.0 / max(probe, 1e-6))))
+    total = sum(one_step() for _ in range(steps))
+    return dict(value=n * steps / total, unit="env-steps/s", cores=nthreads, kind="port",
+                sample="%d envs x %d steps of the C restatement (oracle/*.c, fp64, pthreads), action generation excluded; "
+                       "the Python reference itself cannot run on the GPU box (no /root/reference, no pygame/gym): "
+                       "it measured ~4.9e3 env-steps/s/core single-agent in the build container (BASELINE.md section 2)" % (n, steps),
+                ms_per_step=1e3 * total / steps, steps=steps, envs=n)
+
+
+def reference_main(args, info):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = args.steps if args.cpu_steps == 0 else args.cpu_steps
+    # keep the whole run within a few minutes whatever --steps says
+    base = cpu_arm(args, info, steps_hint=0)
+    line = {"impl": "reference", "metric": "env-steps/s", "value": base["value"], "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": base["steps"], "warmup": 3, "ms_per_step": base["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": info["name"], "envs_per_step_sample": base["envs"], "requested_steps": steps},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    info = workload_info(args)
+    if args.impl == "reference":
+        return reference_main(args, info)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.envs
+    if info["kind"] == "sa":
+        from gym_highway_b200 import HighwayVecEnv
+        env = HighwayVecEnv(n, continuous=info["continuous"], seed=0, device=dev, env_id0=rank * n)
+        A = 1
+    else:
+        from gym_highway_b200 import HighwayMAVecEnv
+        A = args.agents
+        env = HighwayMAVecEnv(n, num_agents=A, continuous=info["continuous"], seed=0, device=dev, env_id0=rank * n)
+
+    # synthetic actions, i.i.d. uniform, generated on device, one buffer per step of a ring
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    ring = 8
+    if info["continuous"]:
+        shape = (ring, n, 2) if info["kind"] == "sa" else (ring, n, A, 2)
+        acts = torch.rand(shape, generator=g, device=dev) * 2 - 1
+    else:
+        shape = (ring, n) if info["kind"] == "sa" else (ring, n, A)
+        acts = torch.randint(0, 4, shape, generator=g, device=dev, dtype=torch.int32)
+
+    working_set = n * info["bytes_per_step"]
+    flush = (not args.no_flush) and working_set < 2 * L2_BYTES
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if flush else None
+
+    # decorrelate the batch first: a few hundred steps so that episodes are at different phases
+    env.rollout_random(150, action_ctr0=0) if hasattr(env, "rollout_random") else None
+    for w in range(max(args.warmup, 3)):
+        env.step_async(acts[w % ring]); env.step_wait()
+    torch.cuda.synchronize(dev)
+
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        if flush:
+            flush_buf.fill_(k & 0xFF)
+        starts[k].record()
+        env.step_async(acts[k % ring])
+        ends[k].record()
+        env.step_wait()
+    torch.cuda.synchronize(dev)
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.result()
+    if world > 1:
+        dist.barrier()
+    dev_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+    total_ms = float(dev_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * n * args.steps / (total_ms * 1e-3)
+
+    # end to end through the host-buffer C-ABI call: pinned host actions in, host obs/rew/done out
+    e2e = None
+    if hasattr(env, "step_host"):
+        h_acts = acts.cpu().numpy()
+        e2e_steps = max(10, min(args.steps, 100))
+        for w in range(3):
+            env.step_host(h_acts[w % ring])
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            env.step_host(h_acts[k % ring])
+        torch.cuda.synchronize(dev)
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        act_bytes = int(h_acts[0].nbytes)
+        out_bytes = n * A * (4 * A + 14 if info["kind"] == "ma" else 18) * 4 + n * A * 4 + n * A
+        e2e = {"value": world * n * e2e_steps / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
+               "d2h_bytes_per_step": out_bytes, "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
+               "api": "HighwayVecEnv.step_host -> hw_sa_step_host (C ABI, host buffers, copies + stream drain inside)"}
+
+    stats = env.episode_statistics() if hasattr(env, "episode_statistics") else {}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        avg_launch_s = float(dev_ms.mean()) * 1e-3
+        achieved = n * info["bytes_per_step"] / avg_launch_s / 1e9
+        line = {
+            "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": info["dtype"], "data": "synthetic",
+            "config": {"workload": info["name"], "envs_per_gpu": n, "ticks_per_step": 9,
+                       "l2": "flushed between timed launches (256 MiB overwrite outside the event pairs)" if flush
+                             else "working set larger than L2, no flush",
+                       "parallelism": "independent env shards, %d rank(s), no data-path collective" % world},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "sa_step_kernel" if info["kind"] == "sa" else "ma_step_kernel",
+                         "algorithmic_bytes_per_env_step": info["bytes_per_step"],
+                         "avg_launch_us": avg_launch_s * 1e6, "min_launch_us": float(dev_ms.min()) * 1e3},
+            "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
+            "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            "episodes": stats,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = {k: v for k, v in cpu_arm(args, info).items() if k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

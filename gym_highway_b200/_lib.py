@@ -1,0 +1,109 @@
+"""ctypes binding of the C ABI declared in include/highway_b200.h.
+
+There is deliberately no fallback: if libhighway_b200.so is missing or does not export the ABI this
+module raises, and every env in this package with it.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhighway_b200.so")
+
+ABI_VERSION = 1
+
+FLAG_CONTINUOUS = 1
+FLAG_NO_INF_OBS = 2
+FLAG_NO_AUTORESET = 4
+
+SA_OBS_DIM = 18
+
+
+class HwSimParams(C.Structure):
+    _fields_ = [("dt", C.c_double), ("ticks_per_step", C.c_int32), ("timeout_tick", C.c_int32)]
+
+
+class HwSaState(C.Structure):
+    _fields_ = [("car_a", C.c_void_p), ("car_b", C.c_void_p), ("obst", C.c_void_p), ("stat", C.c_void_p)]
+
+
+class HwSaOut(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("rew", C.c_void_p), ("done", C.c_void_p), ("term", C.c_void_p),
+                ("stats", C.c_void_p)]
+
+
+class HwMaState(C.Structure):
+    _fields_ = [("cars", C.c_void_p), ("obst", C.c_void_p), ("head", C.c_void_p),
+                ("num_agents", C.c_int32), ("num_slots", C.c_int32)]
+
+
+class HwMaOut(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("rew", C.c_void_p), ("done", C.c_void_p), ("term", C.c_void_p),
+                ("stats", C.c_void_p)]
+
+
+class HighwayLibraryError(RuntimeError):
+    pass
+
+
+_EXPORTS = {
+    # name: (restype, argtypes)
+    "hw_abi_version": (C.c_int, []),
+    "hw_error_string": (C.c_char_p, [C.c_int]),
+    "hw_sa_reset": (C.c_int, [C.POINTER(HwSaState), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hw_sa_step": (C.c_int, [C.POINTER(HwSaState), C.c_void_p, C.POINTER(HwSaOut), C.POINTER(HwSimParams),
+                             C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
+    "hw_sa_observe": (C.c_int, [C.POINTER(HwSaState), C.c_void_p, C.c_int64, C.c_void_p]),
+    "hw_sa_rollout_random": (C.c_int, [C.POINTER(HwSaState), C.POINTER(HwSaOut), C.POINTER(HwSimParams),
+                                       C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+    "hw_sa_step_host": (C.c_int, [C.POINTER(HwSaState), C.c_void_p, C.c_void_p, C.POINTER(HwSaOut),
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HwSimParams),
+                                  C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_EXPORTS)
+
+
+def load():
+    """dlopen the library and bind every declared entry point (raises if anything is missing)"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HighwayLibraryError(
+            "%s is missing: build it with `python -m gym_highway_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _EXPORTS.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise HighwayLibraryError("%s does not export %s" % (LIB_PATH, name))
+        fn.restype = res
+        fn.argtypes = args
+    if lib.hw_abi_version() != ABI_VERSION:
+        raise HighwayLibraryError("ABI version mismatch: library %d, binding %d" % (lib.hw_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().hw_error_string(rc)
+        raise HighwayLibraryError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def sim_params(real_time=False):
+    """dt, ticks per env.step and the time-out tick exactly as the reference derives them:
+    ticks = 60 if real_time else 36 (multi_lane_sim.py:358), dt = 1/ticks (:888),
+    int(ticks/4) ticks per step (highway_env.py:101), done when the accumulated run_time >= 60 (:910-913)."""
+    ticks = 60.0 if real_time else 36.0
+    dt = 1.0 / ticks
+    run_time, t = 0.0, 0
+    while not run_time >= 60:
+        run_time += dt
+        t += 1
+    return HwSimParams(dt, int(ticks / 4), t)

@@ -1,0 +1,102 @@
+// Shared device helpers for the highway step kernels (sm_100a).
+//
+// Arithmetic contract: the reference computes every tick in Python floats (fp64), one rounding per
+// binary operation.  The kernels therefore promote the fp32 state to fp64 registers, use the
+// explicitly rounded intrinsics (__dadd_rn/__dmul_rn/__ddiv_rn are never contracted into FMAs) and
+// round once when the state is stored back.  The file is additionally compiled with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hw {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kDeg2Rad = kPi / 180.0;  // math.radians(x) = x * (pi/180)
+constexpr double kRad2Deg = 180.0 / kPi;  // math.degrees(x) = x * (180/pi)
+
+constexpr uint32_t kBitLeft = 1u << 18, kBitRight = 1u << 19, kBitDoAcc = 1u << 20, kBitDoMaint = 1u << 21;
+
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// python max(lo, min(x, hi)): min keeps x unless hi < x, max keeps lo unless inner > lo
+__device__ __forceinline__ double py_clamp(double x, double lo, double hi)
+{
+    const double inner = (hi < x) ? hi : x;
+    return (inner > lo) ? inner : lo;
+}
+
+__device__ __forceinline__ double lane_centre(int k)  // k = lane-1: 1.25, 3.75, 6.25
+{
+    return 1.25 + 2.5 * (double)k;  // exact in binary
+}
+
+// pygame Rect stores ints; assigning a float truncates toward zero
+__device__ __forceinline__ int rect_x(double px) { return __double2int_rz(dsub(dmul(px, 32.0), 38.0)); }
+__device__ __forceinline__ int rect_y(double py) { return __double2int_rz(dsub(dmul(py, 32.0), 19.0)); }
+
+__device__ __forceinline__ bool rects_overlap(int ax, int ay, int bx, int by)
+{
+    return ax < bx + 76 && ay < by + 38 && ax + 76 > bx && ay + 38 > by;
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11) -------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// CPython random(): (a>>5, b>>6) -> (a*2^26 + b) / 2^53
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b)
+{
+    return dmul(dadd(dmul((double)(a >> 5), 67108864.0), (double)(b >> 6)), 1.0 / 9007199254740992.0);
+}
+
+constexpr uint32_t kSpawnTag = 0x48574159u;   // "HWAY": obstacle respawn stream
+constexpr uint32_t kActionTag = 0x41435421u;  // "ACT!": in-kernel random-action stream
+
+__device__ __forceinline__ void spawn_uniforms(uint64_t seed, uint64_t env_id, uint32_t spawn_ctr, double &u_pos, double &u_vel)
+{
+    const uint4 w = philox4x32_10(make_uint4(spawn_ctr, (uint32_t)env_id, (uint32_t)(env_id >> 32), kSpawnTag),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    u_pos = u53(w.x, w.y);
+    u_vel = u53(w.z, w.w);
+}
+
+// python round(x, 3) as an integer count of 1/1000: nearest integer to the EXACT product x*1000,
+// ties (on the exact value) to even.  p + e == x*1000 exactly (e from the FMA residual).
+__device__ __forceinline__ int round_milli(double x)
+{
+    const double p = dmul(x, 1000.0);
+    const double e = __fma_rn(x, 1000.0, -p);
+    double k = rint(p);
+    if (fabs(dsub(p, k)) == 0.5 && e != 0.0) k = (e > 0.0) ? ceil(p) : floor(p);
+    return (int)k;
+}
+
+// value python would return for round(x, 3), given k = round_milli(x)
+__device__ __forceinline__ double milli_to_reward(int k, double x)
+{
+    return (k == 0) ? copysign(0.0, x) : ddiv((double)k, 1000.0);
+}
+
+// np.clip(ob, low, high) then (ob - low) / (high - low), all in float32 (gym Box stores float32 bounds)
+__device__ __forceinline__ float norm_f32(double raw, float lo, float hi)
+{
+    float v = (float)raw;  // numpy.array(..., dtype=float32): round to nearest
+    v = (v < lo) ? lo : v;
+    v = (v > hi) ? hi : v;
+    return __fdiv_rn(__fsub_rn(v, lo), __fsub_rn(hi, lo));
+}
+
+}  // namespace hw

@@ -1,0 +1,128 @@
+/* highway_b200 — C ABI of the B200-native batched gym-highway step path.
+ *
+ * The reference (sahilPereira/gym-highway) is pure Python and has no FFI of its own; the seam a
+ * maintainer would bind is the per-env gym API and the baselines VecEnv API above it:
+ *   reset()      gym_highway/envs/highway_env.py:121-129, multiagent_envs/highway_env.py:107-112,
+ *                baselines/common/vec_env/dummy_vec_env.py:59-63
+ *   step()       gym_highway/envs/highway_env.py:70-114, highway_env_cont.py:42-55,
+ *                multiagent_envs/highway_env.py:63-99, highway_ma_c_env.py:56-82,
+ *                baselines/common/vec_env/dummy_vec_env.py:46-57 (auto-reset on done),
+ *                dummy_vec_ma_env.py:66-79 (reset when any agent is done)
+ *   get_state()  gym_highway/envs/multi_lane_sim.py:1051-1092, multiagent_envs/simple_base.py:82-154
+ *   Monitor      baselines/bench/monitor.py:58-79 (episode return / length on the terminal step)
+ * Each entry point below replaces one of those calls for a whole batch of environments; the ctypes
+ * binding the Python host uses is gym_highway_b200/_lib.py, and INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only.  Unless a parameter says HOST, every pointer is a
+ * DEVICE pointer into caller-owned memory (the library allocates nothing and keeps no global
+ * state).  Calls are asynchronous with respect to the host and ordered on `stream` (a cudaStream_t
+ * passed as void*; NULL = default stream), except the *_host calls which return after the stream
+ * has drained.  Return value: 0 on success, a cudaError_t (> 0) if the launch failed, or one of the
+ * negative HW_E_* codes for bad arguments.  Re-entrant for disjoint states; no host threads.
+ */
+#ifndef HIGHWAY_B200_H
+#define HIGHWAY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HW_ABI_VERSION 1
+
+#define HW_E_BADARG (-1)   /* null pointer / non-positive size / unsupported combination */
+#define HW_E_ALIGN  (-2)   /* a 16-byte-aligned pointer was required */
+
+/* step flags */
+#define HW_FLAG_CONTINUOUS   1  /* actions are float[.][2] in [-1,1] instead of int32 in {0..3} */
+#define HW_FLAG_NO_INF_OBS   2  /* inf_obs=False: obstacles are never respawned */
+#define HW_FLAG_NO_AUTORESET 4  /* leave terminal states in place (gym per-env semantics) */
+
+/* discrete actions, gym_highway/envs/highway_env.py:14-20 */
+#define HW_ACT_LEFT 0
+#define HW_ACT_RIGHT 1
+#define HW_ACT_ACCELERATE 2
+#define HW_ACT_MAINTAIN 3
+
+#define HW_SA_OBS_DIM 18
+
+/* bit layout of the packed per-car word (HwSaState.car_b[i].w, HwMaState car word 8) */
+#define HW_BITS_TICK_MASK   0xFFFFu  /* single-agent only: simulator ticks since reset */
+#define HW_BITS_LANE_SHIFT  16       /* lane id 1..3 */
+#define HW_BIT_LEFT         (1u << 18)
+#define HW_BIT_RIGHT        (1u << 19)
+#define HW_BIT_DO_ACC       (1u << 20)
+#define HW_BIT_DO_MAINT     (1u << 21)
+
+/* simulation clock, derived exactly as the reference does (multi_lane_sim.py:358,371,888,910-913):
+ * dt = 1/ticks, ticks_per_step = int(ticks/4), timeout_tick = first tick whose accumulated
+ * run_time >= 60 s.  (36 Hz: 1/36, 9, 2160; real_time 60 Hz: 1/60, 15, 3600.) */
+typedef struct HwSimParams {
+    double dt;
+    int32_t ticks_per_step;
+    int32_t timeout_tick;
+} HwSimParams;
+
+/* Single-agent state, structure of arrays, 96 bytes per environment, every array 16-byte aligned.
+ *   car_a[i] = {px, py, raw_x, vx}                      float4
+ *   car_b[i] = {acc, steer, cruise_vel, bits}           float4 (w reinterpreted as uint32)
+ *   obst[k*n + i] = {px, raw_x, vx, init_vx}            float4, k = lane-1 (the lane's newest obstacle)
+ *   stat[i] = {n_obs_collisions, spawn_ctr, episode_return_milli (int32), episode_len}  uint4
+ */
+typedef struct HwSaState {
+    float *car_a;
+    float *car_b;
+    float *obst;
+    uint32_t *stat;
+} HwSaState;
+
+/* Outputs of one step.  `term` rows are written only for environments whose episode ended in this
+ * step: {tick, n_obs_collisions, episode_return_milli, episode_len} (what Monitor reports).
+ * `stats` (nullable) accumulates over calls: [0] episodes ended, [1] sum of episode lengths,
+ * [2] sum of episode returns in milli-reward (two's complement), [3] sum of obstacle collisions,
+ * [4] episodes ended by time-out, [5..7] reserved. */
+typedef struct HwSaOut {
+    float *obs;      /* [n][18], post-reset observation where done */
+    float *rew;      /* [n] */
+    uint8_t *done;   /* [n] */
+    int32_t *term;   /* [n][4], nullable */
+    unsigned long long *stats; /* [8], nullable */
+} HwSaOut;
+
+int hw_abi_version(void);
+const char *hw_error_string(int code);
+
+/* reset(): environments whose mask byte is non-zero (mask NULL = all) go back to the start grid
+ * (highway_env.py:55-65); obs (nullable) receives their reset observation. */
+int hw_sa_reset(const HwSaState *state, const uint8_t *mask, float *obs, int64_t n, void *stream);
+
+/* step(): `actions` is int32[n] (discrete) or float[n][2] (HW_FLAG_CONTINUOUS).  Spawn uniforms of
+ * environment i come from Philox4x32-10 keyed by (seed, env_id0 + i, spawn_ctr). */
+int hw_sa_step(const HwSaState *state, const void *actions, const HwSaOut *out, const HwSimParams *params,
+               uint64_t seed, uint64_t env_id0, int64_t n, int flags, void *stream);
+
+/* get_state(): observation of the current state, no side effects. */
+int hw_sa_observe(const HwSaState *state, float *obs, int64_t n, void *stream);
+
+/* `steps` consecutive step() calls in ONE launch with i.i.d. uniform random actions drawn in-kernel
+ * (Philox stream keyed by (seed ^ action tag, env, action_ctr0 + t)); state stays in registers
+ * between steps, only the last step's outputs are stored.  Used by the random-action benchmark
+ * and by warm-up ("roll the batch forward"). */
+int hw_sa_rollout_random(const HwSaState *state, const HwSaOut *out, const HwSimParams *params,
+                         uint64_t seed, uint64_t env_id0, uint64_t action_ctr0, int steps,
+                         int64_t n, int flags, void *stream);
+
+/* Host-buffer step: HOST actions -> device -> step -> HOST obs/rew/done, all on `stream`, returns
+ * after the copies have landed.  d_actions and d_out are caller-owned DEVICE staging buffers of the
+ * same shapes; h_* should be page-locked for full copy bandwidth. */
+int hw_sa_step_host(const HwSaState *state, const void *h_actions, void *d_actions, const HwSaOut *d_out,
+                    float *h_obs, float *h_rew, uint8_t *h_done, const HwSimParams *params,
+                    uint64_t seed, uint64_t env_id0, int64_t n, int flags, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIGHWAY_B200_H */

@@ -1,0 +1,53 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/highway_b200.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "highway_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gym_highway_b200 import build, _lib
+    build.build()
+    names = _declared()
+    assert "hw_sa_step" in names and "hw_sa_reset" in names and len(names) >= 6
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert sorted(_lib.exported_symbols()) == names
+    assert _lib.load().hw_abi_version() == _lib.ABI_VERSION
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    from gym_highway_b200 import _lib
+    lib = _lib.load()
+    st = _lib.HwSaState(0, 0, 0, 0)
+    assert lib.hw_sa_reset(ctypes.byref(st), None, None, 16, None) == -1
+    st = _lib.HwSaState(16, 16, 16, 16)
+    assert lib.hw_sa_reset(ctypes.byref(st), None, None, 0, None) == -1
+    st = _lib.HwSaState(8, 16, 16, 16)
+    assert lib.hw_sa_reset(ctypes.byref(st), None, None, 4, None) == -2
+    assert b"aligned" in lib.hw_error_string(-2)
+
+
+def test_sim_params_follow_the_reference_clock():
+    from gym_highway_b200 import _lib
+    p = _lib.sim_params(False)
+    assert (p.dt, p.ticks_per_step, p.timeout_tick) == (1.0 / 36.0, 9, 2160)
+    p = _lib.sim_params(True)
+    assert (p.dt, p.ticks_per_step) == (1.0 / 60.0, 15) and p.timeout_tick in (3600, 3601)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from gym_highway_b200 import _lib
+    import pytest
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.HighwayLibraryError):
+        _lib.load()

@@ -1,0 +1,77 @@
+"""CPU: the C oracle must reproduce the reference-generated golden transitions bit for bit."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from helpers import bits_equal, load_golden, sa_state_from_golden
+
+
+def test_philox_known_answers_via_spawn_stream():
+    # the uniform pair of (seed, env, ctr) must be reproducible and in [0, 1)
+    u1, u2 = orc.spawn_uniforms(0, 0, 0)
+    v1, v2 = orc.spawn_uniforms(0, 0, 0)
+    assert (u1, u2) == (v1, v2) and 0.0 <= u1 < 1.0 and 0.0 <= u2 < 1.0
+    assert orc.spawn_uniforms(0, 0, 1) != (u1, u2) and orc.spawn_uniforms(0, 1, 0) != (u1, u2)
+    assert orc.spawn_uniforms(1, 0, 0) != (u1, u2)
+
+
+@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime"])
+def test_sa_oracle_matches_reference_golden(name):
+    g = load_golden(name)
+    cont, rt, seed = bool(g["continuous"]), bool(g["real_time"]), int(g["seed"])
+    n = len(g["out_done"])
+    st = sa_state_from_golden(g)
+    assert np.array_equal(g["env_id"], np.arange(n))  # transition i was recorded as environment i
+    out_all = orc.sa_step(st, g["action"], continuous=cont, real_time=rt, seed=seed, env_id0=0,
+                          autoreset=False, want_next=True)
+    ncoll, ctr = st.ncoll, st.spawn_ctr
+    assert bits_equal(out_all["next_car"], g["out_car"])
+    assert bits_equal(out_all["next_obst"], g["out_obst"])
+    assert np.array_equal(out_all["next_lft"], g["out_lft"])
+    assert bits_equal(out_all["obs"], g["out_obs"])
+    assert bits_equal(out_all["rew"], g["out_rew"].astype(np.float64))
+    assert np.array_equal(out_all["done"], g["out_done"])
+    assert np.array_equal(ncoll, g["out_ncoll"])
+    assert np.array_equal(ctr, g["out_spawn_ctr"].astype(np.uint32))
+    assert g["out_done"].sum() >= 3
+
+
+def test_sa_reset_observation_anchor():
+    # SURVEY.md section 8c sanity anchor (seed 0 reset observation of the reference)
+    st = orc.SaState(3)
+    obs = orc.sa_reset(st)
+    want = np.array([0.5, 0.5, 0.0166667, 0.46875, 0.1666667, 0.34375, 0.125, 0.5, 0.0, 0.65625, 0.5, 0.5,
+                     0.675, 0.5, 0.625, 0.5, 0.65, 0.5], np.float32)
+    assert np.allclose(obs, want[None], atol=1e-6)
+    assert st.lane.tolist() == [2, 2, 2] and st.tick.tolist() == [0, 0, 0]
+
+
+def test_sa_first_steps_anchor():
+    # rewards of actions [2,2,2,0,3,1] from reset, time-out at step 240
+    st = orc.SaState(1)
+    orc.sa_reset(st)
+    rews = []
+    for a in [2, 2, 2, 0, 3, 1]:
+        o = orc.sa_step(st, [a], seed=0)
+        rews.append(float(o["rew"][0]))
+    assert rews == [-0.998, -0.993, -0.985, -0.974, -0.912, -0.849]
+    st = orc.SaState(1)
+    orc.sa_reset(st)
+    for t in range(240):
+        o = orc.sa_step(st, [3], seed=0, autoreset=False)
+        assert bool(o["done"][0]) == (t == 239)
+    assert st.tick[0] == 2160
+
+
+def test_sa_threads_and_quantise_are_consistent():
+    rng = np.random.RandomState(0)
+    n = 257
+    a = orc.SaState(n); orc.sa_reset(a)
+    b = a.copy()
+    for t in range(60):
+        act = rng.randint(0, 4, n)
+        oa = orc.sa_step(a, act, seed=3, quantise=True, nthreads=1)
+        ob = orc.sa_step(b, act, seed=3, quantise=True, nthreads=4)
+        assert bits_equal(oa["obs"], ob["obs"]) and np.array_equal(oa["done"], ob["done"])
+    assert bits_equal(a.car, b.car) and bits_equal(a.obst, b.obst)
+    assert np.array_equal(a.car, a.car.astype(np.float32).astype(np.float64))

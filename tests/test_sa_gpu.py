@@ -1,0 +1,174 @@
+"""GPU parity: the sm_100a single-agent kernels (called through the C ABI) against the C oracle and the
+reference-generated golden transitions.  Bar: every discrete quantity (lane, mode flags, tick,
+collision counters, done, reset) and - because the kernel evaluates the tick in fp64 exactly like the
+oracle - every float (state, observation, reward) bit-exact; the float comparisons additionally
+assert the contract tolerance of 1e-5 relative so that a last-bit libm difference would be reported
+as such rather than hidden."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from helpers import bits_equal, canonical, f32, load_golden, sa_state_from_canonical, sa_state_from_golden
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north_star: positions, velocities and rewards within 1e-5 relative per step
+
+
+def _env(n, **kw):
+    from gym_highway_b200 import HighwayVecEnv
+    return HighwayVecEnv(n, **kw)
+
+
+def _load_state(env, st):
+    from gym_highway_b200.layout import pack_sa
+    p = pack_sa(canonical(st))
+    env.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+
+
+def _read_state(env):
+    from gym_highway_b200.layout import unpack_sa
+    sd = {k: v.cpu().numpy() for k, v in env.state_dict().items()}
+    return sa_state_from_canonical(unpack_sa(sd["car_a"], sd["car_b"], sd["obst"], sd["stat"]))
+
+
+def _assert_close_and_report(name, got, want):
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    denom = np.maximum(np.abs(want), 1e-3)
+    rel = np.abs(got - want) / denom
+    assert rel.max() <= REL_TOL, "%s: max rel err %.3g" % (name, rel.max())
+    nbad = int(np.sum(f32(got).view(np.uint32) != f32(want).view(np.uint32)))
+    assert nbad == 0, "%s: %d of %d values differ in the last bits (max rel %.3g)" % (name, nbad, got.size, rel.max())
+
+
+def test_reset_observation_matches_oracle():
+    env = _env(1000)
+    obs = env.reset().cpu().numpy()
+    st = orc.SaState(1000)
+    want = orc.sa_reset(st)
+    assert bits_equal(obs, want)
+    got = _read_state(env)
+    assert bits_equal(got.car, st.car) and bits_equal(got.obst, st.obst)
+    assert np.array_equal(got.lane, st.lane) and np.array_equal(got.tick, st.tick)
+
+
+@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime"])
+def test_golden_transitions(name):
+    """reference-recorded transitions: one env per transition, env_id taken from the file"""
+    g = load_golden(name)
+    cont, rt, seed = bool(g["continuous"]), bool(g["real_time"]), int(g["seed"])
+    n = len(g["out_done"])
+    assert np.array_equal(g["env_id"], np.arange(n))  # transition i was recorded as environment i
+    env = _env(n, continuous=cont, real_time=rt, seed=seed, env_id0=0, auto_reset=False)
+    _load_state(env, sa_state_from_golden(g))
+    obs, rew, done, _ = env.step(torch.from_numpy(np.ascontiguousarray(g["action"])).cuda())
+    got = _read_state(env)
+    _assert_close_and_report(name + " car", got.car, f32(g["out_car"]))
+    _assert_close_and_report(name + " obst", got.obst, f32(g["out_obst"]))
+    assert np.array_equal(got.lane, g["out_lft"][:, 0]) and np.array_equal(got.flags, g["out_lft"][:, 1])
+    assert np.array_equal(got.tick, g["out_lft"][:, 2])
+    assert np.array_equal(got.ncoll, g["out_ncoll"])
+    assert np.array_equal(got.spawn_ctr, g["out_spawn_ctr"].astype(np.uint32))
+    assert np.array_equal(done.cpu().numpy(), g["out_done"])
+    _assert_close_and_report(name + " obs", obs.cpu().numpy(), g["out_obs"])
+    _assert_close_and_report(name + " rew", rew.cpu().numpy(), f32(g["out_rew"]))
+
+
+@pytest.mark.parametrize("continuous,real_time", [(False, False), (True, False), (False, True)])
+def test_trajectory_parity_1000_steps(continuous, real_time):
+    """4096 envs x 1000 consecutive steps with auto-reset, kernel vs oracle on the same actions"""
+    n, steps, seed = 4096, 1000, 5
+    env = _env(n, continuous=continuous, real_time=real_time, seed=seed, env_id0=100)
+    st = orc.SaState(n)
+    orc.sa_reset(st)
+    rng = np.random.RandomState(1)
+    ndone = 0
+    for t in range(steps):
+        if continuous:
+            act = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        else:
+            act = rng.randint(0, 4, n).astype(np.int32)
+        obs, rew, done, infos = env.step(torch.from_numpy(act).cuda())
+        want = orc.sa_step(st, act, continuous=continuous, real_time=real_time, seed=seed, env_id0=100,
+                           quantise=True, nthreads=8)
+        d = done.cpu().numpy()
+        assert np.array_equal(d, want["done"]), "done differs at step %d" % t
+        assert bits_equal(obs.cpu().numpy(), want["obs"]), "obs differs at step %d" % t
+        assert bits_equal(rew.cpu().numpy(), f32(want["rew"])), "reward differs at step %d" % t
+        ndone += int(d.sum())
+        if d.any():
+            term = env._out[env._cur]["term"].cpu().numpy()
+            assert np.array_equal(term[d].astype(np.int64), want["term"][d])
+        if t % 50 == 49 or t == steps - 1:
+            got = _read_state(env)
+            for f in got.FIELDS:
+                a, b = getattr(got, f), getattr(st, f)
+                assert np.array_equal(a, b), "state field %s differs at step %d" % (f, t)
+    assert ndone > n  # crashes and time-outs both happened
+    s = env.episode_statistics()
+    assert s["episodes"] == ndone
+
+
+def test_tail_block_and_small_batches():
+    for n in (1, 2, 31, 127, 129, 1000):
+        env = _env(n, seed=9)
+        st = orc.SaState(n); orc.sa_reset(st)
+        rng = np.random.RandomState(n)
+        for t in range(30):
+            act = rng.randint(0, 4, n).astype(np.int32)
+            obs, rew, done, _ = env.step(act)
+            want = orc.sa_step(st, act, seed=9, quantise=True)
+            assert bits_equal(obs.cpu().numpy(), want["obs"])
+            assert np.array_equal(done.cpu().numpy(), want["done"])
+
+
+def test_vecenv_contract():
+    from gym_highway_b200 import AlreadySteppingError, NotSteppingError
+    env = _env(8, return_numpy=True)
+    assert env.num_envs == 8 and env.observation_space.shape == (18,) and env.action_space.n == 4
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (8, 18) and obs.dtype == np.float32
+    with pytest.raises(NotSteppingError):
+        env.step_wait()
+    env.step_async(np.zeros(8, np.int64))
+    with pytest.raises(AlreadySteppingError):
+        env.step_async(np.zeros(8, np.int64))
+    obs, rew, done, infos = env.step_wait()
+    assert rew.dtype == np.float32 and done.dtype == bool and len(infos) == 8
+    assert set(infos[0]) == {"run_time", "num_obs_collisions", "num_agent_collisions"}
+    assert infos[0]["run_time"] == 0.25000000000000006
+    with pytest.raises(AssertionError):
+        env.step(np.zeros(7, np.int64))
+    # run a full time-out episode: 240 steps of MAINTAIN from reset, done on the last, obs is the reset obs
+    env = _env(2, return_numpy=True)
+    first = env.reset().copy()
+    for t in range(240):
+        obs, rew, done, infos = env.step([3, 3])
+        assert bool(done[0]) == (t == 239)
+    assert np.array_equal(obs, first)
+    ep = infos[0]["episode"]
+    assert ep["l"] == 240 and infos[0]["run_time"] >= 60.0 and infos.episodes()[0]["l"] == 240
+    env.close(); env.close()
+
+
+def test_host_buffer_step_matches_device_step():
+    n = 513
+    a, b = _env(n, seed=2), _env(n, seed=2)
+    rng = np.random.RandomState(0)
+    for t in range(20):
+        act = rng.randint(0, 4, n).astype(np.int32)
+        o1, r1, d1, _ = a.step(torch.from_numpy(act).cuda())
+        o2, r2, d2 = b.step_host(act)
+        assert bits_equal(o1.cpu().numpy(), o2) and bits_equal(r1.cpu().numpy(), r2)
+        assert np.array_equal(d1.cpu().numpy(), d2)
+
+
+def test_rollout_random_is_deterministic_and_sane():
+    a, b = _env(2048, seed=4), _env(2048, seed=4)
+    oa, ra, da = a.rollout_random(37, action_ctr0=5)
+    ob, rb, db = b.rollout_random(37, action_ctr0=5)
+    assert bits_equal(oa.cpu().numpy(), ob.cpu().numpy())
+    o = oa.cpu().numpy()
+    assert np.isfinite(o).all() and o.min() >= 0.0 and o.max() <= 1.0
