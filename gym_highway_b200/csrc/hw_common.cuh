@@ -90,13 +90,25 @@ __device__ __forceinline__ double milli_to_reward(int k, double x)
     return (k == 0) ? copysign(0.0, x) : ddiv((double)k, 1000.0);
 }
 
-// np.clip(ob, low, high) then (ob - low) / (high - low), all in float32 (gym Box stores float32 bounds)
-__device__ __forceinline__ float norm_f32(double raw, float lo, float hi)
+// np.clip(ob, low, high) then (ob - low) / (high - low), all in float32 (gym Box stores float32 bounds).
+// The span is a compile-time constant.  Power-of-two spans divide exactly by multiplication; for the
+// others (10, 40, 60, 120, 1200) the quotient is computed as q0 = x*rc, q = fma(fma(-q0, c, x), rc, q0)
+// with rc = RN(1/c), which equals the IEEE-rounded x/c for x == 0 and for every float x in [1e-30, c]
+// (verified exhaustively on the host for each constant, scripts/verify_div_by_const.c); x = v - lo
+// cannot fall into (0, 1e-30) unless lo == 0, where GUARD_TINY keeps the IEEE division for that range.
+template <bool GUARD_TINY = false>
+__device__ __forceinline__ float norm_f32(double raw, const float lo, const float hi)
 {
     float v = (float)raw;  // numpy.array(..., dtype=float32): round to nearest
     v = (v < lo) ? lo : v;
     v = (v > hi) ? hi : v;
-    return __fdiv_rn(__fsub_rn(v, lo), __fsub_rn(hi, lo));
+    const float x = __fsub_rn(v, lo);
+    const float c = hi - lo;  // exact for every bound pair of the observation space
+    if (c == 8.f || c == 16.f) return __fmul_rn(x, 1.0f / c);
+    const float rc = 1.0f / c;  // folded at compile time: RN(1/c)
+    if (GUARD_TINY && x < 1e-30f && x != 0.f) return __fdiv_rn(x, c);
+    const float q0 = __fmul_rn(x, rc);
+    return __fmaf_rn(__fmaf_rn(-q0, c, x), rc, q0);
 }
 
 }  // namespace hw

@@ -18,13 +18,16 @@ namespace hw {
 
 constexpr int kSaBlock = 128;
 
+// Per-environment working set (registers).  ovx[] (each obstacle's velocity after its last update) is
+// only materialised at the step boundaries: inside a step it is init_vx, or the car's vx for the one
+// obstacle that is being held back (`slow`), so the tick loop carries a flag instead of three doubles.
 struct SaEnv {
     double px, py, rx, vx, acc, steer, cruise;
     double opx[3], orx[3], ovx[3], oiv[3];
+    double odt[3];  // oiv[k] * dt, the per-tick displacement of an obstacle that is not held back
     uint32_t bits;  // tick | lane << 16 | mode flags
-    uint32_t ncoll, spawn_ctr;
-    int ep_ret_milli;
-    uint32_t ep_len;
+    uint32_t spawn_ctr;
+    bool slow;      // the obstacle in the car's lane moved with min(init_vx, car vx) == car vx in the last tick
 };
 
 struct SaPtrs {
@@ -36,13 +39,13 @@ __device__ __forceinline__ void sa_load(SaEnv &e, const SaPtrs &S, int64_t i, in
 {
     const float4 a = S.car_a[i], b = S.car_b[i];
     const float4 o0 = S.obst[i], o1 = S.obst[n + i], o2 = S.obst[2 * n + i];
-    const uint4 s = S.stat[i];
     e.px = a.x; e.py = a.y; e.rx = a.z; e.vx = a.w;
     e.acc = b.x; e.steer = b.y; e.cruise = b.z; e.bits = __float_as_uint(b.w);
     e.opx[0] = o0.x; e.orx[0] = o0.y; e.ovx[0] = o0.z; e.oiv[0] = o0.w;
     e.opx[1] = o1.x; e.orx[1] = o1.y; e.ovx[1] = o1.z; e.oiv[1] = o1.w;
     e.opx[2] = o2.x; e.orx[2] = o2.y; e.ovx[2] = o2.z; e.oiv[2] = o2.w;
-    e.ncoll = s.x; e.spawn_ctr = s.y; e.ep_ret_milli = (int)s.z; e.ep_len = s.w;
+    e.spawn_ctr = reinterpret_cast<const uint32_t *>(S.stat)[4 * i + 1];  // the other counters are touched once, at the end
+    e.slow = false;
 }
 
 __device__ __forceinline__ void sa_store(const SaEnv &e, const SaPtrs &S, int64_t i, int64_t n)
@@ -52,10 +55,9 @@ __device__ __forceinline__ void sa_store(const SaEnv &e, const SaPtrs &S, int64_
     S.obst[i] = make_float4((float)e.opx[0], (float)e.orx[0], (float)e.ovx[0], (float)e.oiv[0]);
     S.obst[n + i] = make_float4((float)e.opx[1], (float)e.orx[1], (float)e.ovx[1], (float)e.oiv[1]);
     S.obst[2 * n + i] = make_float4((float)e.opx[2], (float)e.orx[2], (float)e.ovx[2], (float)e.oiv[2]);
-    S.stat[i] = make_uint4(e.ncoll, e.spawn_ctr, (uint32_t)e.ep_ret_milli, e.ep_len);
 }
 
-// start grid, highway_env.py:55-65; spawn_ctr survives so that every episode sees fresh obstacles
+// start grid, highway_env.py:55-65
 __device__ __forceinline__ void sa_reset_env(SaEnv &e)
 {
     e.px = 20.0; e.py = 3.75; e.rx = 20.0; e.vx = 0.0;
@@ -64,129 +66,227 @@ __device__ __forceinline__ void sa_reset_env(SaEnv &e)
     e.opx[0] = -20.0; e.orx[0] = -20.0; e.ovx[0] = 7.0; e.oiv[0] = 7.0;
     e.opx[1] = -25.0; e.orx[1] = -25.0; e.ovx[1] = 5.0; e.oiv[1] = 5.0;
     e.opx[2] = -40.0; e.orx[2] = -40.0; e.ovx[2] = 6.0; e.oiv[2] = 6.0;
-    e.ncoll = 0; e.ep_ret_milli = 0; e.ep_len = 0;
+    e.slow = false;
 }
+
+// exact slow path of the collision test (generic car rect); only reached when an obstacle is within
+// about one car length in x, or for states the reference cannot produce (car px != 10 after the first tick)
+__device__ __noinline__ int sa_collide_exact(double px, double py, double o0, double o1, double o2)
+{
+    const int ax = rect_x(px), ay = rect_y(py);
+    return (rects_overlap(ax, ay, rect_x(o0), 21) ? 1 : 0) + (rects_overlap(ax, ay, rect_x(o1), 101) ? 1 : 0)
+         + (rects_overlap(ax, ay, rect_x(o2), 181) ? 1 : 0);
+}
+
+// tan(x) = x + x*z*p(z), z = x*x, for |x| <= 0.55 rad (python clamps |steering| to 30 deg = 0.5236 rad).
+// p = near-minimax fit of (tan x - x)/x^3 (mpmath chebyfit, 12 terms, |error| < 4e-19 relative to tan),
+// Horner in FMAs: no range reduction, no special cases; within 1 ulp of libm's tan.
+__constant__ double kTanC[12] = {
+    0x1.20f68de6f5b19p-15, 0x1.790a294731d86p-16, 0x1.b8cea70623061p-14, 0x1.f054fa543c93bp-13,
+    0x1.3598d277c0b71p-11, 0x1.7d9f32bbba0bcp-10, 0x1.d6d3fe7809e9dp-9,  0x1.226e34c1e860cp-7,
+    0x1.664f48853966bp-6,  0x1.ba1ba1ba167cdp-5,  0x1.1111111111133p-3,  0x1.5555555555555p-2};
+
+__device__ __forceinline__ double tan_small(double x)
+{
+    const double z = x * x;
+    double p = kTanC[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = __fma_rn(p, z, kTanC[i]);
+    return __fma_rn(x * z, p, x);
+}
+
+// road clamp of Car.update_d (:219-222, lower bound 0) / update_c (:169-172, lower bound 1)
+template <bool CONT>
+__device__ __forceinline__ double road_clamp(double y)
+{
+    const double lo = CONT ? 1.0 : 0.0;
+    const double hi = (7.0 < y) ? 7.0 : y;  // min(y, 7), only applied when y > 6
+    return (y < lo) ? lo : ((y > 6.0) ? hi : y);
+}
+
+// hi word of a double; for non-negative values the unsigned order of hi words is the numeric order
+__device__ __forceinline__ uint32_t hi32(double x) { return (uint32_t)__double2hiint(x); }
+
+// a, b or c for lane 1, 2, 3: plain 32-bit selects on the two halves (keeps ptxas from branching)
+__device__ __forceinline__ double sel_lane(const bool l1, const bool l2, const double a, const double b, const double c)
+{
+    const int hi = l1 ? __double2hiint(a) : (l2 ? __double2hiint(b) : __double2hiint(c));
+    const int lo = l1 ? __double2loint(a) : (l2 ? __double2loint(b) : __double2loint(c));
+    return __hiloint2double(hi, lo);
+}
+
+// per-launch constants, computed on the host with the same IEEE operations python performs
+struct SaConsts {
+    double dt;       // 1/ticks
+    double k30dt;    // 30.0 * dt   (moveLeft / moveRight steering increment)
+    int ticks_per_step;
+    int timeout_tick;
+};
 
 // One simulator tick (multi_lane_sim.py:879-1049).  Returns the number of obstacle rects the car
 // overlapped (0 when the collision lock is on); the tick reward is -250*n, or vx/20-1 when n == 0.
-template <bool CONT>
-__device__ __forceinline__ int sa_tick(SaEnv &e, const double dt, const double k30dt, const bool inf_obs,
-                                       const int act_d, const double a0_5dt, const double a1_30dt,
+//
+// Written for instruction count: with i.i.d. random actions practically every warp holds lanes in every
+// mode, so divergent branches cost the sum of both sides plus BSSY/BSYNC; the modes are therefore
+// evaluated with selects, and only genuinely rare events (an obstacle within a car length, a respawn) or
+// long ones (the steering path with its tan and two divisions) stay behind branches.  FIRST = first tick
+// of the step, the only one that can see the collision lock or a car that is not yet pinned at x = 10.
+template <bool CONT, bool FIRST>
+__device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaConsts &K, const bool inf_obs,
+                                       const uint32_t amask, const uint32_t apair, const double a0_5dt, const double a1_30dt,
                                        const uint64_t seed, const uint64_t env_id)
 {
-    const uint32_t tick0 = e.bits & HW_BITS_TICK_MASK;
-    e.bits += 1;  // tick field lives in the low 16 bits; 2160 (or 3600) never carries out
-    int lane = (int)((e.bits >> HW_BITS_LANE_SHIFT) & 3u);
+    const double dt = K.dt;
+    const bool lock = FIRST && (e.bits & HW_BITS_TICK_MASK) == 0;  // collision_count_lock: first tick after reset
+    const double px = FIRST ? e.px : 10.0;
+    uint32_t b = e.bits + 1;  // tick field lives in the low 16 bits; 2160 (or 3601) never carries out
+    int lane = (int)((b >> HW_BITS_LANE_SHIFT) & 3u);
 
     // ---- apply action (multi_lane_sim.py:502-526) ----
+    uint32_t fire = 0;
     if (CONT) {
         e.acc = py_clamp(dadd(e.acc, a0_5dt), -5.0, 5.0);
         e.steer = py_clamp(dadd(e.steer, a1_30dt), -30.0, 30.0);
     } else {
-        if (act_d == HW_ACT_ACCELERATE && !(e.bits & kBitDoAcc)) {
-            e.bits = (e.bits | kBitDoAcc) & ~kBitDoMaint;
-        } else if (act_d == HW_ACT_MAINTAIN && !(e.bits & kBitDoMaint)) {
-            // nearest vehicle strictly ahead in the car's lane; each lane holds exactly one obstacle
-            const double fpx = (lane == 1) ? e.opx[0] : (lane == 2) ? e.opx[1] : e.opx[2];
-            const double fvx = (lane == 1) ? e.ovx[0] : (lane == 2) ? e.ovx[1] : e.ovx[2];
-            e.cruise = (fpx > e.px) ? fvx : e.vx;
-            e.bits = (e.bits | kBitDoMaint) & ~kBitDoAcc;
-        }
+        // amask = the mode bit the action wants (LEFT/RIGHT/ACCELERATE/MAINTAIN); it "fires" when not already set,
+        // which sets the bit and clears the other bit of its pair (apair = both bits of the pair)
+        fire = amask & ~b;
+        b = (b & ~(fire ? apair : 0u)) | fire;
+        lane += ((fire & kBitRight) && lane < 3) ? 1 : 0;
+        lane -= ((fire & kBitLeft) && lane > 1) ? 1 : 0;
         e.acc = py_clamp(e.acc, -5.0, 5.0);
-        if (act_d == HW_ACT_RIGHT && !(e.bits & kBitRight)) {
-            lane = min(lane + 1, 3);
-            e.bits = (e.bits | kBitRight) & ~kBitLeft;
-        } else if (act_d == HW_ACT_LEFT && !(e.bits & kBitLeft)) {
-            lane = max(lane - 1, 1);
-            e.bits = (e.bits | kBitLeft) & ~kBitRight;
-        }
         e.steer = py_clamp(e.steer, -30.0, 30.0);
     }
+    // the obstacle that shares the car's lane (each lane holds exactly one).  A tick never fires both a lane
+    // change and MAINTAIN, so the post-action lane is also the lane maintain() looks at.
+    bool l1 = lane == 1, l2 = lane == 2;
+    double fpx = sel_lane(l1, l2, e.opx[0], e.opx[1], e.opx[2]);
+    double fiv = sel_lane(l1, l2, e.oiv[0], e.oiv[1], e.oiv[2]);
+    if (!CONT) {
+        // maintain(): cruise = velocity of the nearest vehicle strictly ahead in the lane, else own velocity.  That
+        // velocity is what its last update left: the stored one on the first tick, else init_vx or the car's vx.
+        double fvx;
+        if (FIRST) fvx = sel_lane(l1, l2, e.ovx[0], e.ovx[1], e.ovx[2]);
+        else       fvx = e.slow ? e.vx : fiv;
+        const double cr = (fpx > px) ? fvx : e.vx;
+        e.cruise = (fire & kBitDoMaint) ? cr : e.cruise;
+    }
 
-    // ---- collision test on the rects the previous tick left (:920-937); skipped on the first tick ----
+    // ---- collision test on the rects the previous tick left (:920-937) ----
+    // The car's rect x is 282 whenever px == 10 (always, after its first update), so an obstacle overlaps in x
+    // iff 207 <= trunc(opx*32-38) <= 357 iff 7.65625 <= opx < 12.375.  The filter below is a superset of
+    // that interval taken on the hi words (positive doubles order like their bit patterns); the exact integer
+    // rect test runs only for the few lanes that pass it.
     int ncol = 0;
-    if (tick0 != 0) {
-        const int ax = rect_x(e.px), ay = rect_y(e.py);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) ncol += rects_overlap(ax, ay, rect_x(e.opx[k]), 21 + 80 * k) ? 1 : 0;
-        e.ncoll += ncol;
+    if (!lock) {
+        constexpr uint32_t kLo = 0x401EA000u, kSpan = 0x4028C000u - 0x401EA000u;  // hi(7.65625), hi(12.375)
+        const bool near = (hi32(e.opx[0]) - kLo <= kSpan) || (hi32(e.opx[1]) - kLo <= kSpan) || (hi32(e.opx[2]) - kLo <= kSpan);
+        if (near || (FIRST && px != 10.0)) {
+            ncol = sa_collide_exact(px, e.py, e.opx[0], e.opx[1], e.opx[2]);
+            ncoll_acc += ncol;
+        }
     }
 
     // ---- car update (:140-229) ----
     if (!CONT) {
-        if (e.bits & kBitDoAcc) {
-            e.acc = (e.acc < 0.0) ? 0.0 : dadd(e.acc, dt);
-            if (e.acc == 5.0) e.bits &= ~kBitDoAcc;
-        } else if (e.bits & kBitDoMaint) {
-            const double vc = ceil(e.vx), cc = ceil(e.cruise);
-            e.acc = (vc <= cc) ? 5.0 : -5.0;
-            if (vc == cc) { e.vx = e.cruise; e.acc = 0.0; e.bits &= ~kBitDoMaint; }
-        }
+        const bool m_acc = (b & kBitDoAcc) != 0;
+        const bool m_maint = (b & kBitDoMaint) != 0;  // never set together with do_accelerate
+        // accelerate(): acc = 0 if acc < 0 else acc + dt ; `acc == 5.0` clears the mode
+        const double acc_a = (e.acc < 0.0) ? 0.0 : dadd(e.acc, dt);
+        // maintain(): bang-bang towards ceil(cruise), snap when the ceilings agree
+        const double vc = ceil(e.vx), cc = ceil(e.cruise);
+        const bool snap = m_maint && vc == cc;
+        const double acc_m = snap ? 0.0 : ((vc <= cc) ? 5.0 : -5.0);
+        e.acc = m_acc ? acc_a : (m_maint ? acc_m : e.acc);
+        e.vx = snap ? e.cruise : e.vx;
+        if (m_acc && e.acc == 5.0) b &= ~kBitDoAcc;
+        if (snap) b &= ~kBitDoMaint;
     }
     e.vx = py_clamp(dadd(e.vx, dmul(e.acc, dt)), 0.0, 20.0);
     if (!CONT) {
-        const double ty = lane_centre(lane - 1);
-        if (e.bits & kBitLeft) {
-            e.steer = dadd(e.steer, k30dt);
-            if (e.py <= ty) { e.steer = 0.0; e.bits &= ~kBitLeft; }
-        } else if (e.bits & kBitRight) {
-            e.steer = dsub(e.steer, k30dt);
-            if (e.py >= ty) { e.steer = 0.0; e.bits &= ~kBitRight; }
-        }
+        const double ty = __hiloint2double(l1 ? 0x3FF40000 : (l2 ? 0x400E0000 : 0x40190000), 0);  // 1.25, 3.75, 6.25
+        const bool m_left = (b & kBitLeft) != 0;
+        const bool m_right = (b & kBitRight) != 0;  // never set together with left_mode
+        // adding +0.0 is the identity on every value steer can hold (it is never -0.0)
+        e.steer = dadd(e.steer, m_left ? K.k30dt : (m_right ? -K.k30dt : 0.0));
+        const bool reached = (m_left && e.py <= ty) || (m_right && e.py >= ty);
+        if (reached) { e.steer = 0.0; b &= ~(kBitLeft | kBitRight); }
     }
-    double ang = 0.0;
-    if (e.steer != 0.0) ang = ddiv(e.vx, ddiv(4.0, tan(dmul(e.steer, kDeg2Rad))));
     const double vdt = dmul(e.vx, dt);
-    // position += velocity * dt with velocity.y == 0: py + 0.0 == py for every py the clamps can produce
-    if (CONT) e.py = dsub(e.py, dmul(ang, dt));
-    else      e.py = dsub(e.py, dmul(dmul(dmul(ang, kRad2Deg), dt), dt));
-    e.px = 10.0;  // the only car is always the leader
-    if (CONT) { if (e.py < 1.0) e.py = 1.0; else if (e.py > 6.0) e.py = (7.0 < e.py) ? 7.0 : e.py; }
-    else      { if (e.py < 0.0) e.py = 0.0; else if (e.py > 6.0) e.py = (7.0 < e.py) ? 7.0 : e.py; }
+    if (e.steer != 0.0) {
+        // angular_velocity = vx / (length / tan(radians(steering))); 4/t == 4 * (1/t) exactly (power of two)
+        const double radius = dmul(4.0, __drcp_rn(tan_small(dmul(e.steer, kDeg2Rad))));
+        const double ang = ddiv(e.vx, radius);
+        // position += velocity * dt has velocity.y == 0: py + 0.0 == py for every py the clamps can produce
+        if (CONT) e.py = dsub(e.py, dmul(ang, dt));
+        else      e.py = dsub(e.py, dmul(dmul(dmul(ang, kRad2Deg), dt), dt));
+    }
+    e.py = road_clamp<CONT>(e.py);  // with ang == 0, py - 0.0 == py: only the clamp can move it
     e.rx = dadd(e.rx, vdt);
     if (CONT) {  // lane = nearest lane centre, first minimum wins
         const double d0 = fabs(dsub(e.py, 1.25)), d1 = fabs(dsub(e.py, 3.75)), d2 = fabs(dsub(e.py, 6.25));
-        const double m = fmin(d0, fmin(d1, d2));
-        lane = (d0 == m) ? 1 : (d1 == m) ? 2 : 3;
+        lane = (d0 <= d1 && d0 <= d2) ? 1 : (d1 <= d2) ? 2 : 3;
+        l1 = lane == 1; l2 = lane == 2;
+        fpx = sel_lane(l1, l2, e.opx[0], e.opx[1], e.opx[2]);
+        fiv = sel_lane(l1, l2, e.oiv[0], e.oiv[1], e.oiv[2]);
     }
-    e.bits = (e.bits & ~(3u << HW_BITS_LANE_SHIFT)) | ((uint32_t)lane << HW_BITS_LANE_SHIFT);
+    e.bits = (b & ~(3u << HW_BITS_LANE_SHIFT)) | ((uint32_t)lane << HW_BITS_LANE_SHIFT);
 
-    // ---- obstacle update (:324-347): sees the leader's post-update lane, position and velocity ----
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        double v = py_clamp(e.oiv[k], -20.0, 20.0);
-        if (k + 1 == lane && e.opx[k] < 10.0) v = (e.vx < e.oiv[k]) ? e.vx : e.oiv[k];
-        e.ovx[k] = v;
-        const double odt = dmul(v, dt);
-        e.opx[k] = dsub(dadd(e.opx[k], odt), vdt);
-        e.orx[k] = dadd(e.orx[k], odt);
-    }
-
-    // ---- respawn (:963-991) ----
-    if (inf_obs) {
+    // ---- obstacle update (:324-347): sees the leader's post-update lane, position (10) and velocity ----
+    // velocity.x = max(-20, min(init_vx, 20)) is the identity: init_vx is 5..7 by construction (start grid, U[5,7)).
+    // Only the obstacle in the car's lane can be held back: v = min(init_vx, car vx) when it is behind the car.
+    e.slow = fpx < 10.0 && e.vx < fiv;
+    {
+        const int held = e.slow ? lane : 0;  // lane of the held-back obstacle, 0 = none
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            if (e.opx[k] < -2.375) {
-                double u1, u2;
-                spawn_uniforms(seed, env_id, e.spawn_ctr, u1, u2);
-                e.spawn_ctr += 1;
-                const double x = dadd(70.0, dmul(30.0, u1));
-                const double v = dadd(5.0, dmul(2.0, u2));
-                e.opx[k] = x;
-                e.orx[k] = dadd(e.rx, dsub(x, 10.0));
-                e.ovx[k] = v;
-                e.oiv[k] = v;
+            const double d = (held == k + 1) ? vdt : e.odt[k];  // v * dt
+            e.opx[k] = dsub(dadd(e.opx[k], d), vdt);
+            e.orx[k] = dadd(e.orx[k], d);
+        }
+    }
+
+    // ---- respawn (:963-991): opx < -2.375, pre-filtered on the hi words (negative doubles order reversed) ----
+    if (inf_obs) {
+        constexpr uint32_t kNeg = 0xC0030000u;  // hi(-2.375); hi >= kNeg  <=>  opx <= -2.375 (- a few ulps of slack)
+        if (max(max(hi32(e.opx[0]), hi32(e.opx[1])), hi32(e.opx[2])) >= kNeg) {
+            // lanes in ascending order; x = U(70,100) then v = U(5,7) from one Philox block per spawn
+#pragma unroll 1
+            for (int k = 0; k < 3; ++k) {
+                const double o = (k == 0) ? e.opx[0] : (k == 1) ? e.opx[1] : e.opx[2];
+                if (o < -2.375) {
+                    double u1, u2;
+                    spawn_uniforms(seed, env_id, e.spawn_ctr, u1, u2);
+                    e.spawn_ctr += 1;
+                    const double x = dadd(70.0, dmul(30.0, u1));
+                    const double v = dadd(5.0, dmul(2.0, u2));
+                    const double r = dadd(e.rx, dsub(x, 10.0));  // leader.raw_x + (x - leader.x), the leader sits at x = 10
+                    const double d = dmul(v, dt);
+                    if (k == 0) { e.opx[0] = x; e.orx[0] = r; e.oiv[0] = v; e.odt[0] = d; }
+                    else if (k == 1) { e.opx[1] = x; e.orx[1] = r; e.oiv[1] = v; e.odt[1] = d; }
+                    else { e.opx[2] = x; e.orx[2] = r; e.oiv[2] = v; e.odt[2] = d; }
+                }
             }
+            // a fresh obstacle is far ahead (x >= 70): it cannot be the held-back one
+            e.slow = e.slow && sel_lane(l1, l2, e.opx[0], e.opx[1], e.opx[2]) < 10.0;
         }
     }
     return ncol;
+}
+
+// velocities of the obstacles after their last update, materialised for the observation and the stored state
+__device__ __forceinline__ void sa_materialise_ovx(SaEnv &e)
+{
+    const int lane = (int)((e.bits >> HW_BITS_LANE_SHIFT) & 3u);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) e.ovx[k] = (e.slow && lane == k + 1) ? e.vx : e.oiv[k];
 }
 
 // observation pairs (x, y) j = 0..8 -> obs[2j], obs[2j+1]; float32 clip + normalise
 __device__ __forceinline__ void sa_observe(const SaEnv &e, float2 *row)
 {
     row[0] = make_float2(norm_f32(e.acc, -5.f, 5.f), norm_f32(e.steer, -30.f, 30.f));
-    row[1] = make_float2(norm_f32(e.rx, 0.f, 1200.f), norm_f32(e.py, 0.f, 8.f));
+    row[1] = make_float2(norm_f32<true>(e.rx, 0.f, 1200.f), norm_f32(e.py, 0.f, 8.f));
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         row[2 + k] = make_float2(norm_f32(dsub(e.orx[k], e.rx), -60.f, 60.f),
@@ -196,45 +296,71 @@ __device__ __forceinline__ void sa_observe(const SaEnv &e, float2 *row)
     row[5] = make_float2(norm_f32(e.vx, -20.f, 20.f), 0.5f);
 }
 
-// shared-memory staged, fully coalesced store of a block's observations ([kSaBlock][18] floats)
-__device__ __forceinline__ void store_obs_block(const float *sm, float *obs, int64_t block_base, int64_t n)
+// One warp's observations (32 rows x 18 floats = 2304 contiguous bytes in global memory) go through a
+// warp-private shared-memory tile: each lane writes its row as nine 8-byte words (conflict-free: the row
+// stride is 9 words of 8 bytes, odd), then the warp streams the tile out as 144 coalesced 16-byte stores.
+// Only __syncwarp() is needed, so warps never wait for each other.
+__device__ __forceinline__ void store_obs_warp(float *sm_tile, float *__restrict__ obs, int64_t warp_base, int64_t n)
 {
-    const int64_t rows = min((int64_t)kSaBlock, n - block_base);
-    const int nvec = (int)(rows * HW_SA_OBS_DIM / 4);  // rows*18 floats; rows*18*4 bytes, 16 B multiple iff rows even
-    float4 *dst = reinterpret_cast<float4 *>(obs + block_base * HW_SA_OBS_DIM);
-    const float4 *src = reinterpret_cast<const float4 *>(sm);
-    for (int v = threadIdx.x; v < nvec; v += kSaBlock) dst[v] = src[v];
-    const int tail0 = nvec * 4, total = (int)(rows * HW_SA_OBS_DIM);
-    for (int f = tail0 + threadIdx.x; f < total; f += kSaBlock) obs[block_base * HW_SA_OBS_DIM + f] = sm[f];
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    const int64_t rows = min((int64_t)32, n - warp_base);
+    float *dst = obs + warp_base * HW_SA_OBS_DIM;
+    if (rows == 32) {
+        const float4 *src = reinterpret_cast<const float4 *>(sm_tile);
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) d4[lane + 32 * v] = src[lane + 32 * v];
+        if (lane < 16) d4[lane + 128] = src[lane + 128];
+    } else {
+        for (int f = lane; f < (int)rows * HW_SA_OBS_DIM; f += 32) dst[f] = sm_tile[f];
+    }
 }
 
+// Resident blocks per SM the register allocator is asked to make room for (measured on B200 at 4M envs:
+// discrete 5 -> 7.9e9, 6 -> 8.5e9, 8 -> 8.5e9 env-steps/s; continuous 6 -> 8.8e9, 8 -> 9.2e9).
+#ifndef HW_SA_MIN_BLOCKS_D
+#define HW_SA_MIN_BLOCKS_D 6
+#endif
+#ifndef HW_SA_MIN_BLOCKS_C
+#define HW_SA_MIN_BLOCKS_C 8
+#endif
+
 template <bool CONT, bool RANDOM_ACTIONS>
-__global__ void __launch_bounds__(kSaBlock)
+__global__ void __launch_bounds__(kSaBlock, CONT ? HW_SA_MIN_BLOCKS_C : HW_SA_MIN_BLOCKS_D)
 sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew,
                uint8_t *__restrict__ done, int4 *__restrict__ term, unsigned long long *__restrict__ stats,
-               const HwSimParams P, const uint64_t seed, const uint64_t env_id0, const uint64_t action_ctr0,
+               const SaConsts K, const uint64_t seed, const uint64_t env_id0, const uint64_t action_ctr0,
                const int steps, const int64_t n, const int flags)
 {
     __shared__ __align__(16) float sm_obs[kSaBlock * HW_SA_OBS_DIM];
-    const int64_t block_base = (int64_t)blockIdx.x * kSaBlock;
-    const int64_t i = block_base + threadIdx.x;
-    const bool valid = i < n;
+    const int64_t i = (int64_t)blockIdx.x * kSaBlock + threadIdx.x;
+    const int64_t warp_base = i - (threadIdx.x & 31);
+    float *sm_tile = sm_obs + (threadIdx.x >> 5) * 32 * HW_SA_OBS_DIM;
+    if (warp_base >= n) return;  // whole warp out of range
     const bool inf_obs = !(flags & HW_FLAG_NO_INF_OBS);
     const bool autoreset = !(flags & HW_FLAG_NO_AUTORESET);
-    const double dt = P.dt;
-    const double k30dt = dmul(30.0, dt);
+    const double dt = K.dt;
 
-    if (valid) {
+    if (i < n) {
         SaEnv e;
         sa_load(e, S, i, n);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) e.odt[k] = dmul(e.oiv[k], dt);
         const uint64_t env_id = env_id0 + (uint64_t)i;
 
+        // episode accounting (Monitor) lives outside the tick loop
+        uint32_t ncoll_step = 0;       // obstacle collisions counted during this launch (since the last reset)
+        int ret_milli_step = 0;        // rounded rewards since the last reset inside this launch, in 1/1000
+        uint32_t len_step = 0;         // steps since the last reset inside this launch
+        bool was_reset = false;        // an auto-reset happened inside this launch
         double reward = 0.0;
         int rew_milli = 0;
         bool is_done = false;
         for (int s = 0; s < steps; ++s) {
             int act_d = 0;
             double a0_5dt = 0.0, a1_30dt = 0.0;
+            uint32_t amask = 0, apair = 0;
             if (RANDOM_ACTIONS) {
                 const uint64_t aseed = seed ^ 0x9E3779B97F4A7C15ull;
                 const uint64_t c = action_ctr0 + (uint64_t)s;
@@ -256,40 +382,59 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
             } else {
                 act_d = reinterpret_cast<const int *>(actions)[i];
             }
-
-            // env.step: up to ticks_per_step ticks, stop at the first crash (highway_env.py:99-108)
-            int ncol = 0;
-            for (int t = 0; t < P.ticks_per_step; ++t) {
-                ncol = sa_tick<CONT>(e, dt, k30dt, inf_obs, act_d, a0_5dt, a1_30dt, seed, env_id);
-                if (ncol > 0) break;
+            if (!CONT) {  // ACTION_LOOKUP (highway_env.py:14-20) as the mode bit it requests
+                amask = (act_d == HW_ACT_LEFT) ? kBitLeft : (act_d == HW_ACT_RIGHT) ? kBitRight
+                      : (act_d == HW_ACT_ACCELERATE) ? kBitDoAcc : (act_d == HW_ACT_MAINTAIN) ? kBitDoMaint : 0u;
+                apair = (amask & (kBitLeft | kBitRight)) ? (kBitLeft | kBitRight) : (kBitDoAcc | kBitDoMaint);
             }
+            // env.step: up to ticks_per_step ticks, stop at the first crash (highway_env.py:99-108)
+            int ncol = sa_tick<CONT, true>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
+            e.px = 10.0;  // the only car is always the leader (:212-213)
+            for (int t = 1; t < K.ticks_per_step && ncol == 0; ++t)
+                ncol = sa_tick<CONT, false>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
             const uint32_t tick = e.bits & HW_BITS_TICK_MASK;
-            const bool timeout = tick >= (uint32_t)P.timeout_tick;
+            const bool timeout = tick >= (uint32_t)K.timeout_tick;
             is_done = timeout || ncol > 0;
             reward = (ncol > 0) ? -250.0 * (double)ncol : dsub(ddiv(e.vx, 20.0), 1.0);
             rew_milli = round_milli(reward);
-            e.ep_ret_milli += rew_milli;
-            e.ep_len += 1;
+            ret_milli_step += rew_milli;
+            len_step += 1;
+            sa_materialise_ovx(e);
 
             if (is_done) {
-                if (term) term[i] = make_int4((int)tick, (int)e.ncoll, e.ep_ret_milli, (int)e.ep_len);
+                // Monitor / info of the finished episode: state counters + what this launch added
+                const uint4 st = S.stat[i];
+                const uint32_t nc = (was_reset ? 0u : st.x) + ncoll_step;
+                const int er = (was_reset ? 0 : (int)st.z) + ret_milli_step;
+                const uint32_t el = (was_reset ? 0u : st.w) + len_step;
+                if (term) term[i] = make_int4((int)tick, (int)nc, er, (int)el);
                 if (stats) {
                     atomicAdd(&stats[0], 1ull);
-                    atomicAdd(&stats[1], (unsigned long long)e.ep_len);
-                    atomicAdd(&stats[2], (unsigned long long)(long long)e.ep_ret_milli);
-                    atomicAdd(&stats[3], (unsigned long long)e.ncoll);
+                    atomicAdd(&stats[1], (unsigned long long)el);
+                    atomicAdd(&stats[2], (unsigned long long)(long long)er);
+                    atomicAdd(&stats[3], (unsigned long long)nc);
                     if (ncol == 0) atomicAdd(&stats[4], 1ull);
                 }
-                if (autoreset) sa_reset_env(e);
+                if (autoreset) {
+                    sa_reset_env(e);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) e.odt[k] = dmul(e.oiv[k], dt);
+                    was_reset = true; ncoll_step = 0; ret_milli_step = 0; len_step = 0;
+                }
             }
         }
         rew[i] = (float)milli_to_reward(rew_milli, reward);
         done[i] = is_done ? 1 : 0;
-        sa_observe(e, reinterpret_cast<float2 *>(sm_obs) + threadIdx.x * (HW_SA_OBS_DIM / 2));
+        sa_observe(e, reinterpret_cast<float2 *>(sm_tile) + (threadIdx.x & 31) * (HW_SA_OBS_DIM / 2));
         sa_store(e, S, i, n);
+        {   // per-env counters: read-modify-write once per launch
+            uint4 st = S.stat[i];
+            if (was_reset) { st.x = 0; st.z = 0; st.w = 0; }
+            st.x += ncoll_step; st.y = e.spawn_ctr; st.z = (uint32_t)((int)st.z + ret_milli_step); st.w += len_step;
+            S.stat[i] = st;
+        }
     }
-    __syncthreads();
-    if (block_base < n) store_obs_block(sm_obs, obs, block_base, n);
+    store_obs_warp(sm_tile, obs, warp_base, n);
 }
 
 __global__ void __launch_bounds__(kSaBlock)
@@ -299,9 +444,9 @@ sa_reset_kernel(SaPtrs S, const uint8_t *__restrict__ mask, float *__restrict__ 
     if (i >= n) return;
     if (mask && !mask[i]) return;
     SaEnv e;
-    e.spawn_ctr = S.stat[i].y;
     sa_reset_env(e);
     sa_store(e, S, i, n);
+    S.stat[i] = make_uint4(0u, S.stat[i].y, 0u, 0u);  // spawn_ctr survives so that every episode sees fresh obstacles
     if (obs) {
         float2 row[9];
         sa_observe(e, row);
@@ -315,15 +460,16 @@ __global__ void __launch_bounds__(kSaBlock)
 sa_observe_kernel(SaPtrs S, float *__restrict__ obs, const int64_t n)
 {
     __shared__ __align__(16) float sm_obs[kSaBlock * HW_SA_OBS_DIM];
-    const int64_t block_base = (int64_t)blockIdx.x * kSaBlock;
-    const int64_t i = block_base + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kSaBlock + threadIdx.x;
+    const int64_t warp_base = i - (threadIdx.x & 31);
+    float *sm_tile = sm_obs + (threadIdx.x >> 5) * 32 * HW_SA_OBS_DIM;
+    if (warp_base >= n) return;
     if (i < n) {
         SaEnv e;
         sa_load(e, S, i, n);
-        sa_observe(e, reinterpret_cast<float2 *>(sm_obs) + threadIdx.x * (HW_SA_OBS_DIM / 2));
+        sa_observe(e, reinterpret_cast<float2 *>(sm_tile) + (threadIdx.x & 31) * (HW_SA_OBS_DIM / 2));
     }
-    __syncthreads();
-    if (block_base < n) store_obs_block(sm_obs, obs, block_base, n);
+    store_obs_warp(sm_tile, obs, warp_base, n);
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -356,10 +502,15 @@ static int launch_step(const HwSaState *st, const void *actions, const HwSaOut *
     if (steps < 1 || P->ticks_per_step < 1 || P->timeout_tick < 1 || P->timeout_tick > 0xFFFF || !(P->dt > 0.0)) return HW_E_BADARG;
     if (!aligned16(out->obs) || (out->term && !aligned16(out->term))) return HW_E_ALIGN;
     const SaPtrs S = ptrs(st);
+    SaConsts K;
+    K.dt = P->dt;
+    K.k30dt = 30.0 * P->dt;  // python: 30.0 * dt
+    K.ticks_per_step = P->ticks_per_step;
+    K.timeout_tick = P->timeout_tick;
     const unsigned grid = (unsigned)((n + kSaBlock - 1) / kSaBlock);
     int4 *term = reinterpret_cast<int4 *>(out->term);
     const bool cont = (flags & HW_FLAG_CONTINUOUS) != 0;
-#define HW_LAUNCH(C, R) sa_step_kernel<C, R><<<grid, kSaBlock, 0, stream>>>(S, actions, out->obs, out->rew, out->done, term, out->stats, *P, seed, env_id0, action_ctr0, steps, n, flags)
+#define HW_LAUNCH(C, R) sa_step_kernel<C, R><<<grid, kSaBlock, 0, stream>>>(S, actions, out->obs, out->rew, out->done, term, out->stats, K, seed, env_id0, action_ctr0, steps, n, flags)
     if (cont) { if (random_actions) HW_LAUNCH(true, true); else HW_LAUNCH(true, false); }
     else      { if (random_actions) HW_LAUNCH(false, true); else HW_LAUNCH(false, false); }
 #undef HW_LAUNCH

@@ -304,11 +304,6 @@ static void *sa_step_range(void *arg)
         ep_ret_milli[i] += k_milli;
         ep_len[i] += 1;
 
-        if (quant) {
-            e.px = q32(e.px); e.py = q32(e.py); e.rx = q32(e.rx); e.vx = q32(e.vx);
-            e.acc = q32(e.acc); e.steer = q32(e.steer); e.cruise = q32(e.cruise);
-            for (int k = 0; k < 3; ++k) { e.opx[k] = q32(e.opx[k]); e.orx[k] = q32(e.orx[k]); e.ovx[k] = q32(e.ovx[k]); e.oiv[k] = q32(e.oiv[k]); }
-        }
         if (next_car) {
             double *nc = next_car + 7 * (size_t)i;
             nc[0] = e.px; nc[1] = e.py; nc[2] = e.rx; nc[3] = e.vx; nc[4] = e.acc; nc[5] = e.steer; nc[6] = e.cruise;
@@ -322,7 +317,12 @@ static void *sa_step_range(void *arg)
             if (term) { int64_t *tm = term + 4 * (size_t)i; tm[0] = e.tick; tm[1] = e.ncoll; tm[2] = ep_ret_milli[i]; tm[3] = ep_len[i]; }
             if (autoreset) { sa_reset(&e); ep_ret_milli[i] = 0; ep_len[i] = 0; }
         }
-        sa_observe(&e, obs + 18 * (size_t)i);
+        sa_observe(&e, obs + 18 * (size_t)i); /* from the fp64 values, like the reference */
+        if (quant) { /* fp32 storage between steps (what the kernels keep in HBM) */
+            e.px = q32(e.px); e.py = q32(e.py); e.rx = q32(e.rx); e.vx = q32(e.vx);
+            e.acc = q32(e.acc); e.steer = q32(e.steer); e.cruise = q32(e.cruise);
+            for (int k = 0; k < 3; ++k) { e.opx[k] = q32(e.opx[k]); e.orx[k] = q32(e.orx[k]); e.ovx[k] = q32(e.ovx[k]); e.oiv[k] = q32(e.oiv[k]); }
+        }
 
         double *cw = car + 7 * (size_t)i;
         cw[0] = e.px; cw[1] = e.py; cw[2] = e.rx; cw[3] = e.vx; cw[4] = e.acc; cw[5] = e.steer; cw[6] = e.cruise;
