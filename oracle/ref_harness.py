@@ -168,3 +168,106 @@ class RefSingleAgent(object):
             action = int(action)
         with _patched_uniform(provider):
             return self.env.step(action)
+
+
+class RefMultiAgent(object):
+    """one reference MultiAgentEnv / MultiAgentEnvContinuous with state injection (A <= 5 cars)"""
+
+    def __init__(self, num_agents, continuous=False, real_time=False, shared_reward=False):
+        m = load()
+        kw = dict(TRAIN_KW, real_time=real_time)
+        cls = m['ma'].MultiAgentEnvContinuous if continuous else m['ma'].MultiAgentEnv
+        self.env = cls(world_config=kw, num_agents=num_agents, shared_reward=shared_reward)
+        self.world = self.env.world
+        self.A = num_agents
+        self.continuous = continuous
+        self.dt = 1.0 / self.world.ticks
+        from gym_highway.multiagent_envs.agent import Obstacle
+        from gym_highway.multiagent_envs import highway_constants
+        import pygame
+        self._Obstacle, self._K, self._pygame = Obstacle, highway_constants, pygame
+
+    def reset(self):
+        return self.env.reset()
+
+    def inject(self, st, i):
+        """load row i of an oracle MaState into a freshly reset reference world"""
+        self.env.reset()
+        w, A = self.world, self.A
+        cars = list(w.agents)
+        assert [c.id for c in cars] == list(range(A))
+        tick = int(st.tick[i])
+        for a, car in enumerate(cars):
+            px, py, rx, vx, vy, acc, steer, cruise = (float(v) for v in st.car[i, a])
+            car.position.x, car.position.y = px, py
+            car.raw_position.x, car.raw_position.y = rx, py
+            car.velocity.x, car.velocity.y = vx, vy
+            car.acceleration, car.steering, car.cruise_vel = acc, steer, cruise
+            car.lane_id = int(st.lane[i, a])
+            f = int(st.cflags[i, a])
+            car.left_mode, car.right_mode = bool(f & 1), bool(f & 2)
+            car.do_accelerate, car.do_maintain = bool(f & 4), bool(f & 8)
+            if tick > 0:
+                _set_rect(car)
+        obstacles = []
+        for k in range(int(st.nobs[i])):
+            opx, orx, ovx, oiv = (float(v) for v in st.obst[i, k])
+            lane = int(st.olane[i, k])
+            o = self._Obstacle(id=A + lane - 1, x=opx, y=_orc.LANE_C[lane - 1], raw_x=orx, vel_x=ovx, vel_y=0.0,
+                               lane_id=lane, color=self._K.YELLOW)
+            o.init_velocity.x = oiv
+            if not int(st.ofresh[i, k]):
+                _set_rect(o)
+            obstacles.append(o)
+        G = self._pygame.sprite.Group
+        w.scripted_agents = G(*obstacles)
+        w.all_obstacles = G(*(cars + obstacles))
+        ghost = self._Obstacle(id=A, x=1.0e9, y=0.0, vel_x=0.0, lane_id=1)  # a retired lane_max_obs entry: never respawns
+        w.lane_max_obs = [obstacles[int(s)] if int(s) >= 0 else ghost for s in st.newest[i]]
+        w.reference_car = cars[int(st.leader[i])]
+        w.run_time = _run_time_after(tick, self.dt)
+        w.collision_count_lock = (tick == 0)
+        w.num_obs_collisions = int(st.nc_obs[i])
+        w.num_agent_collisions = int(st.nc_agent[i])
+        w.is_done = [False] * A
+
+    def extract(self, st, i):
+        w, A = self.world, self.A
+        cars = list(w.agents)
+        for a, car in enumerate(cars):
+            assert car.raw_position.y == car.position.y
+            st.car[i, a] = (car.position.x, car.position.y, car.raw_position.x, car.velocity.x, car.velocity.y,
+                            car.acceleration, car.steering, car.cruise_vel)
+            st.lane[i, a] = car.lane_id
+            st.cflags[i, a] = (1 * car.left_mode) | (2 * car.right_mode) | (4 * car.do_accelerate) | (8 * car.do_maintain)
+        obstacles = list(w.scripted_agents)
+        assert len(obstacles) <= st.K, "K too small for this trajectory: %d live obstacles" % len(obstacles)
+        st.nobs[i] = len(obstacles)
+        st.obst[i] = 0.0; st.olane[i] = 0; st.ofresh[i] = 0
+        for k, o in enumerate(obstacles):
+            assert o.position.y == _orc.LANE_C[o.lane_id - 1] and o.id == A + o.lane_id - 1 and o.velocity.y == 0.0
+            st.obst[i, k] = (o.position.x, o.raw_position.x, o.velocity.x, o.init_velocity.x)
+            st.olane[i, k] = o.lane_id
+            st.ofresh[i, k] = int(o.rect.y == 0)
+        for lane in range(3):
+            o = w.lane_max_obs[lane]
+            st.newest[i, lane] = obstacles.index(o) if o in obstacles else -1
+        st.leader[i] = w.reference_car.id
+        st.nc_obs[i] = w.num_obs_collisions
+        st.nc_agent[i] = w.num_agent_collisions
+        t, rt = 0, 0.0
+        while rt < w.run_time:
+            rt += self.dt
+            t += 1
+        assert rt == w.run_time
+        st.tick[i] = t
+
+    def step(self, actions, provider):
+        """actions: int[A] (discrete) or float[A][2]; returns (obs_n list of f64 arrays, reward_n, done_n, info)"""
+        if self.continuous:
+            act = [[float(np.float32(a[0])), float(np.float32(a[1]))] for a in actions]
+        else:
+            act = [np.eye(4)[int(a)] for a in actions]
+        with _patched_uniform(provider):
+            ob, r, d, info = self.env.step(act)
+        return ob, list(r), list(d), info

@@ -43,3 +43,17 @@ def bits_equal(a, b):
 
 def f32(x):
     return np.asarray(x, np.float64).astype(np.float32)
+
+
+MA_STATE_FIELDS = ("car", "lane", "cflags", "tick", "leader", "nobs", "obst", "olane", "ofresh", "newest",
+                   "nc_obs", "nc_agent", "spawn_ctr")
+
+
+def ma_state_from_golden(g, prefix="in_"):
+    from oracle import ma_oracle as mo
+    n = len(g["env_id"])
+    st = mo.MaState(n, int(g["num_agents"]), int(g["num_slots"]))
+    for f in MA_STATE_FIELDS:
+        if prefix + f in g:
+            getattr(st, f)[...] = g[prefix + f].reshape(getattr(st, f).shape)
+    return st

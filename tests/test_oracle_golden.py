@@ -75,3 +75,43 @@ def test_sa_threads_and_quantise_are_consistent():
         assert bits_equal(oa["obs"], ob["obs"]) and np.array_equal(oa["done"], ob["done"])
     assert bits_equal(a.car, b.car) and bits_equal(a.obst, b.obst)
     assert np.array_equal(a.car, a.car.astype(np.float32).astype(np.float64))
+
+
+MA_GOLDEN = ["ma1_discrete", "ma1_continuous", "ma3_discrete", "ma3_continuous", "ma5_discrete", "ma5_continuous",
+             "ma5_discrete_shared"]
+
+
+@pytest.mark.parametrize("name", MA_GOLDEN)
+def test_ma_oracle_matches_reference_golden(name):
+    from oracle import ma_oracle as mo
+    from helpers import ma_state_from_golden
+    g = load_golden(name)
+    n = len(g["env_id"])
+    assert np.array_equal(g["env_id"], np.arange(n))
+    st = ma_state_from_golden(g)
+    out = mo.ma_step(st, g["action"], continuous=bool(g["continuous"]), seed=int(g["seed"]), env_id0=0,
+                     autoreset=False, shared_reward=bool(g["shared_reward"]))
+    for f in ("car", "obst"):
+        assert bits_equal(getattr(st, f), g["out_" + f].astype(np.float64)), f
+    for f in ("lane", "cflags", "tick", "leader", "nobs", "olane", "ofresh", "newest", "nc_obs", "nc_agent"):
+        assert np.array_equal(getattr(st, f), g["out_" + f].reshape(getattr(st, f).shape)), f
+    assert np.array_equal(st.spawn_ctr, g["out_spawn_ctr"].astype(np.uint32))
+    assert bits_equal(out["obs"], g["out_obs"])
+    assert bits_equal(out["rew"], g["out_rew"].astype(np.float64))
+    assert np.array_equal(out["done"], g["out_done"])
+    assert st.overflow.max() == 0 and g["out_done"].any(axis=1).sum() >= 3
+
+
+def test_ma_reset_and_threads():
+    from oracle import ma_oracle as mo
+    for A in (1, 3, 5):
+        a = mo.MaState(130, A); obs = mo.ma_reset(a)
+        assert obs.shape == (130, A, 4 * A + 14) and np.isfinite(obs).all()
+        b = a.copy()
+        rng = np.random.RandomState(A)
+        for t in range(40):
+            act = rng.randint(0, 4, (130, A))
+            oa = mo.ma_step(a, act, seed=1, quantise=True, nthreads=1)
+            ob = mo.ma_step(b, act, seed=1, quantise=True, nthreads=4)
+            assert bits_equal(oa["obs"], ob["obs"]) and np.array_equal(oa["done"], ob["done"])
+        assert bits_equal(a.car, b.car) and a.overflow.max() == 0
