@@ -14,6 +14,9 @@ ABI_VERSION = 1
 FLAG_CONTINUOUS = 1
 FLAG_NO_INF_OBS = 2
 FLAG_NO_AUTORESET = 4
+FLAG_SHARED_REWARD = 16
+MA_MAX_AGENTS = 5
+MA_MAX_SLOTS = 16
 
 SA_OBS_DIM = 18
 
@@ -55,6 +58,13 @@ _EXPORTS = {
     "hw_sa_observe": (C.c_int, [C.POINTER(HwSaState), C.c_void_p, C.c_int64, C.c_void_p]),
     "hw_sa_rollout_random": (C.c_int, [C.POINTER(HwSaState), C.POINTER(HwSaOut), C.POINTER(HwSimParams),
                                        C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+    "hw_ma_reset": (C.c_int, [C.POINTER(HwMaState), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hw_ma_step": (C.c_int, [C.POINTER(HwMaState), C.c_void_p, C.POINTER(HwMaOut), C.POINTER(HwSimParams),
+                             C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
+    "hw_ma_observe": (C.c_int, [C.POINTER(HwMaState), C.c_void_p, C.c_int64, C.c_void_p]),
+    "hw_ma_step_host": (C.c_int, [C.POINTER(HwMaState), C.c_void_p, C.c_void_p, C.POINTER(HwMaOut),
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HwSimParams),
+                                  C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
     "hw_sa_step_host": (C.c_int, [C.POINTER(HwSaState), C.c_void_p, C.c_void_p, C.POINTER(HwSaOut),
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HwSimParams),
                                   C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),

@@ -78,23 +78,6 @@ __device__ __noinline__ int sa_collide_exact(double px, double py, double o0, do
          + (rects_overlap(ax, ay, rect_x(o2), 181) ? 1 : 0);
 }
 
-// tan(x) = x + x*z*p(z), z = x*x, for |x| <= 0.55 rad (python clamps |steering| to 30 deg = 0.5236 rad).
-// p = near-minimax fit of (tan x - x)/x^3 (mpmath chebyfit, 12 terms, |error| < 4e-19 relative to tan),
-// Horner in FMAs: no range reduction, no special cases; within 1 ulp of libm's tan.
-__constant__ double kTanC[12] = {
-    0x1.20f68de6f5b19p-15, 0x1.790a294731d86p-16, 0x1.b8cea70623061p-14, 0x1.f054fa543c93bp-13,
-    0x1.3598d277c0b71p-11, 0x1.7d9f32bbba0bcp-10, 0x1.d6d3fe7809e9dp-9,  0x1.226e34c1e860cp-7,
-    0x1.664f48853966bp-6,  0x1.ba1ba1ba167cdp-5,  0x1.1111111111133p-3,  0x1.5555555555555p-2};
-
-__device__ __forceinline__ double tan_small(double x)
-{
-    const double z = x * x;
-    double p = kTanC[0];
-#pragma unroll
-    for (int i = 1; i < 12; ++i) p = __fma_rn(p, z, kTanC[i]);
-    return __fma_rn(x * z, p, x);
-}
-
 // road clamp of Car.update_d (:219-222, lower bound 0) / update_c (:169-172, lower bound 1)
 template <bool CONT>
 __device__ __forceinline__ double road_clamp(double y)

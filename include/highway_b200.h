@@ -40,6 +40,7 @@ extern "C" {
 #define HW_FLAG_CONTINUOUS   1  /* actions are float[.][2] in [-1,1] instead of int32 in {0..3} */
 #define HW_FLAG_NO_INF_OBS   2  /* inf_obs=False: obstacles are never respawned */
 #define HW_FLAG_NO_AUTORESET 4  /* leave terminal states in place (gym per-env semantics) */
+#define HW_FLAG_SHARED_REWARD 16 /* multi-agent: every car receives the sum of the rewards (shared_reward=True) */
 
 /* discrete actions, gym_highway/envs/highway_env.py:14-20 */
 #define HW_ACT_LEFT 0
@@ -48,6 +49,9 @@ extern "C" {
 #define HW_ACT_MAINTAIN 3
 
 #define HW_SA_OBS_DIM 18
+#define HW_MA_MAX_AGENTS 5   /* the reference's start grid holds five cars (simple_base.py:32-38) */
+#define HW_MA_MAX_SLOTS 16   /* live obstacles per environment (three at reset, typically <= 8) */
+#define HW_MA_OBS_DIM(A) (4 * (A) + 14)
 
 /* bit layout of the packed per-car word (HwSaState.car_b[i].w, HwMaState car word 8) */
 #define HW_BITS_TICK_MASK   0xFFFFu  /* single-agent only: simulator ticks since reset */
@@ -119,6 +123,57 @@ int hw_sa_rollout_random(const HwSaState *state, const HwSaOut *out, const HwSim
  * after the copies have landed.  d_actions and d_out are caller-owned DEVICE staging buffers of the
  * same shapes; h_* should be page-locked for full copy bandwidth. */
 int hw_sa_step_host(const HwSaState *state, const void *h_actions, void *d_actions, const HwSaOut *d_out,
+                    float *h_obs, float *h_rew, uint8_t *h_done, const HwSimParams *params,
+                    uint64_t seed, uint64_t env_id0, int64_t n, int flags, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-agent environments: A cars (1..5) and up to K live obstacles (3..16) per environment.
+ *
+ * State, structure of arrays over n environments (i = environment):
+ *   cars[(a*9 + w)*n + i]  32-bit word w of car a: 0 px, 1 py, 2 raw_x, 3 vx, 4 vy, 5 acc, 6 steer,
+ *                          7 cruise_vel (floats), 8 bits (uint32: lane << 16 | HW_BIT_* mode flags)
+ *   obst[(k*n + i)*4 + j]  float4 {px, raw_x, vx, init_vx} of obstacle slot k; slots 0..nobs-1 are live and
+ *                          kept in insertion order (the order pygame's sprite Group iterates); 16-byte aligned
+ *   head[w*n + i]          uint32 words of the per-environment header:
+ *        0  tick (bits 0-15) | leader car << 16 (3 bits) | nobs << 20 (5 bits)
+ *        1  slot of lane_max_obs[lane] for lane 1,2,3: 5 bits each, 31 = that obstacle has been retired
+ *        2  lane id of slot k in bits 2k..2k+1
+ *        3  bit k: slot k still has pygame's default rect (spawned, not yet updated)
+ *           bit 16: a spawn was dropped because all K slots were live; bit 17: a lane had no obstacle to observe
+ *        4  n_obs_collisions  5  n_agent_collisions  6  spawn_ctr  7  episode_len
+ *        8,9  episode return (sum of every car's reward), IEEE double, low word first
+ */
+typedef struct HwMaState {
+    float *cars;
+    float *obst;
+    uint32_t *head;
+    int32_t num_agents;
+    int32_t num_slots;
+} HwMaState;
+
+/* Outputs of one multi-agent step.  `term` rows are written only for environments in which some car
+ * finished (the whole environment resets then, dummy_vec_ma_env.py:74-77):
+ * {tick, n_obs_collisions, n_agent_collisions, episode_return, episode_len} as doubles.
+ * `stats` (nullable) accumulates [0] episodes, [1] sum of lengths, [2] sum of returns in milli-reward,
+ * [3] obstacle collisions, [4] time-outs, [5] car-car collisions, [6] dropped spawns. */
+typedef struct HwMaOut {
+    float *obs;      /* [n][A][4A+14], post-reset observation where any car is done */
+    float *rew;      /* [n][A] */
+    uint8_t *done;   /* [n][A] */
+    double *term;    /* [n][5], nullable */
+    unsigned long long *stats; /* [8], nullable */
+} HwMaOut;
+
+int hw_ma_reset(const HwMaState *state, const uint8_t *mask, float *obs, int64_t n, void *stream);
+
+/* `actions` is int32[n][A] (the argmax of each car's action vector, multiagent_envs/highway_env.py:77-78)
+ * or float[n][A][2] with HW_FLAG_CONTINUOUS (highway_ma_c_env.py:63-64). */
+int hw_ma_step(const HwMaState *state, const void *actions, const HwMaOut *out, const HwSimParams *params,
+               uint64_t seed, uint64_t env_id0, int64_t n, int flags, void *stream);
+
+int hw_ma_observe(const HwMaState *state, float *obs, int64_t n, void *stream);
+
+int hw_ma_step_host(const HwMaState *state, const void *h_actions, void *d_actions, const HwMaOut *d_out,
                     float *h_obs, float *h_rew, uint8_t *h_done, const HwSimParams *params,
                     uint64_t seed, uint64_t env_id0, int64_t n, int flags, void *stream);
 

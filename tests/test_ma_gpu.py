@@ -1,0 +1,122 @@
+"""GPU parity of the multi-agent kernels against the C oracle and the reference-generated goldens."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ma_oracle as mo
+from helpers import MA_STATE_FIELDS, bits_equal, f32, load_golden, ma_state_from_golden
+
+pytestmark = pytest.mark.gpu
+
+MA_GOLDEN = ["ma1_discrete", "ma1_continuous", "ma3_discrete", "ma3_continuous", "ma5_discrete", "ma5_continuous",
+             "ma5_discrete_shared"]
+
+
+def _env(n, A, **kw):
+    from gym_highway_b200 import HighwayMAVecEnv
+    return HighwayMAVecEnv(n, num_agents=A, **kw)
+
+
+def _load_state(env, st):
+    from gym_highway_b200.layout import pack_ma
+    c = {f: getattr(st, f) for f in st.FIELDS}
+    p = pack_ma(c, st.A, st.K)
+    env.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in p.items()})
+
+
+def _read_state(env):
+    from gym_highway_b200.layout import unpack_ma
+    sd = {k: v.cpu().numpy() for k, v in env.state_dict().items()}
+    c = unpack_ma(sd["cars"], sd["obst"], sd["head"], env.num_agents, env.num_slots)
+    st = mo.MaState(env.num_envs, env.num_agents, env.num_slots)
+    for f in st.FIELDS:
+        getattr(st, f)[...] = c[f]
+    return st
+
+
+def _same_bits(name, got, want):
+    got, want = f32(got), f32(want)
+    nbad = int(np.sum(got.view(np.uint32) != want.view(np.uint32)))
+    rel = np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want), 1e-3)
+    assert rel.max() <= 1e-5, "%s: max rel err %.3g" % (name, rel.max())
+    assert nbad == 0, "%s: %d of %d values differ in the last bits" % (name, nbad, got.size)
+
+
+@pytest.mark.parametrize("name", MA_GOLDEN)
+def test_golden_transitions(name):
+    g = load_golden(name)
+    A, K = int(g["num_agents"]), int(g["num_slots"])
+    n = len(g["env_id"])
+    env = _env(n, A, continuous=bool(g["continuous"]), seed=int(g["seed"]), env_id0=0, auto_reset=False,
+               shared_reward=bool(g["shared_reward"]), num_slots=K)
+    _load_state(env, ma_state_from_golden(g))
+    obs, rew, done, _ = env.step(torch.from_numpy(np.ascontiguousarray(g["action"])).cuda())
+    got = _read_state(env)
+    _same_bits(name + " car", got.car, g["out_car"])
+    _same_bits(name + " obst", got.obst, g["out_obst"])
+    for f in ("lane", "cflags", "tick", "leader", "nobs", "olane", "ofresh", "newest", "nc_obs", "nc_agent"):
+        assert np.array_equal(getattr(got, f), g["out_" + f].reshape(getattr(got, f).shape)), f
+    assert np.array_equal(got.spawn_ctr, g["out_spawn_ctr"].astype(np.uint32))
+    assert np.array_equal(done.cpu().numpy(), g["out_done"])
+    _same_bits(name + " obs", obs.cpu().numpy(), g["out_obs"])
+    _same_bits(name + " rew", rew.cpu().numpy(), g["out_rew"])
+    assert int(env.diagnostics().max()) == 0
+
+
+@pytest.mark.parametrize("A,continuous", [(5, False), (5, True), (3, False), (1, True)])
+def test_trajectory_parity(A, continuous):
+    n, steps, seed = 2048, 400, 9
+    env = _env(n, A, continuous=continuous, seed=seed, env_id0=7)
+    st = mo.MaState(n, A)
+    mo.ma_reset(st)
+    rng = np.random.RandomState(2)
+    nd = 0
+    for t in range(steps):
+        if continuous:
+            act = rng.uniform(-1, 1, (n, A, 2)).astype(np.float32)
+            act[:, :, 1] *= 0.1
+        else:
+            act = np.where(rng.rand(n, A) < 0.6, 2, rng.randint(0, 4, (n, A))).astype(np.int32)
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        want = mo.ma_step(st, act, continuous=continuous, seed=seed, env_id0=7, quantise=True, nthreads=8)
+        d = done.cpu().numpy()
+        assert np.array_equal(d, want["done"]), "done differs at step %d" % t
+        assert bits_equal(obs.cpu().numpy(), want["obs"]), "obs differs at step %d" % t
+        assert bits_equal(rew.cpu().numpy(), f32(want["rew"])), "reward differs at step %d" % t
+        anyd = d.any(axis=1)
+        nd += int(anyd.sum())
+        if anyd.any():
+            term = env._out[env._cur]["term"].cpu().numpy()
+            assert np.array_equal(term[anyd], want["term"][anyd])
+        if t % 40 == 39 or t == steps - 1:
+            got = _read_state(env)
+            for f in MA_STATE_FIELDS + ("ep_len", "ep_ret"):
+                assert np.array_equal(getattr(got, f), getattr(st, f)), "state field %s differs at step %d" % (f, t)
+    assert nd > n // 4
+    assert int(env.diagnostics().max()) == 0 and st.overflow.max() == 0
+    assert env.episode_statistics()["episodes"] == nd
+
+
+def test_ma_vecenv_contract():
+    env = _env(4, 5, return_numpy=True)
+    assert env.num_envs == 4 and env.n == 5 and len(env.observation_space) == 5 and env.observation_space[0].shape == (34,)
+    obs = env.reset()
+    assert obs.shape == (4, 5, 34) and obs.dtype == np.float32
+    onehot = np.zeros((4, 5, 4), np.float32); onehot[..., 2] = 1.0
+    obs, rew, done, infos = env.step(onehot)
+    assert rew.shape == (4, 5) and done.shape == (4, 5) and done.dtype == bool and len(infos) == 4
+    assert set(infos[0]['n'][0]) == {"rewards", "run_time", "num_obs_collisions", "num_agent_collisions"}
+    assert abs(infos[0]['n'][0]["rewards"] - (-0.9982638888888888)) < 1e-6
+    with pytest.raises(IndexError):
+        _env(2, 8)
+
+
+def test_ma_host_step_matches_device_step():
+    n, A = 300, 5
+    a, b = _env(n, A, seed=3), _env(n, A, seed=3)
+    rng = np.random.RandomState(0)
+    for t in range(15):
+        act = rng.randint(0, 4, (n, A)).astype(np.int32)
+        o1, r1, d1, _ = a.step(torch.from_numpy(act).cuda())
+        o2, r2, d2 = b.step_host(act)
+        assert bits_equal(o1.cpu().numpy(), o2) and bits_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy(), d2)
