@@ -266,7 +266,8 @@ def main():
         out_bytes = n * A * (4 * A + 14 if info["kind"] == "ma" else 18) * 4 + n * A * 4 + n * A
         e2e = {"value": world * n * e2e_steps / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
                "d2h_bytes_per_step": out_bytes, "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
-               "api": "HighwayVecEnv.step_host -> hw_sa_step_host (C ABI, host buffers, copies + stream drain inside)"}
+               "api": ("HighwayVecEnv.step_host -> hw_sa_step_host" if info["kind"] == "sa" else "HighwayMAVecEnv.step_host -> hw_ma_step_host")
+                      + " (C ABI, host buffers, copies + stream drain inside)"}
 
     stats = env.episode_statistics() if hasattr(env, "episode_statistics") else {}
 

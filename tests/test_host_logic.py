@@ -1,0 +1,137 @@
+"""CPU: host-side logic that needs no GPU — sharding, gloo collectives (world_size 2), GAE / returns / sf01
+against numpy restatements of the baselines runners, spaces and the run-time table."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gym_highway_b200 import distributed as hd
+from gym_highway_b200 import rollout
+from gym_highway_b200.spaces import Box, Discrete, highway_obs_bounds
+
+
+def test_shard_covers_everything_once():
+    for total in (1, 7, 64, 1000, 1048576):
+        for ws in (1, 2, 3, 4, 8):
+            spans = [hd.shard(total, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and sum(n for _, n in spans) == total
+            for (a0, an), (b0, _) in zip(spans, spans[1:]):
+                assert a0 + an == b0
+            assert max(n for _, n in spans) - min(n for _, n in spans) <= 1
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, ws, port, total, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    env_id0, n_local = hd.shard(total, rank, ws)
+    # every rank "finishes" one episode per local env with return -(global id) milli and length id
+    ids = torch.arange(env_id0, env_id0 + n_local)
+    stats = torch.zeros(8, dtype=torch.int64)
+    stats[0] = n_local; stats[1] = ids.sum(); stats[2] = -ids.sum(); stats[3] = rank
+    red = hd.reduce_statistics(stats)
+    roll = torch.arange(3 * n_local, dtype=torch.float32).reshape(3, n_local) + 1000 * rank
+    gat = hd.gather_env_axis(roll, axis=1)
+    mx = hd.max_over_ranks(1.0 + rank)
+    q.put((rank, red.tolist(), tuple(gat.shape), gat[0].tolist(), mx, stats.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world_size_2_statistics_and_gather():
+    ws, total = 2, 10
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, ws, port, total, q)) for r in range(ws)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(ws))
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    ids = np.arange(total)
+    for rank, red, shape, row0, mx, local in res:
+        assert red[0] == total and red[1] == ids.sum() and red[2] == -ids.sum() and red[3] == 1
+        assert shape == (3, total) and mx == 2.0
+        assert row0 == [0.0, 1.0, 2.0, 3.0, 4.0, 1000.0, 1001.0, 1002.0, 1003.0, 1004.0]
+        assert local[0] == 5  # the local counters are left untouched
+    d = hd.statistics_dict(torch.tensor(res[0][1]))
+    assert d["episodes"] == total and abs(d["mean_length"] - 4.5) < 1e-12 and abs(d["mean_return"] + 0.0045) < 1e-12
+
+
+def _np_gae(rew, val, dones, last_val, last_done, gamma, lam):
+    # baselines/ppo2/runner.py:53-65 restated
+    T = rew.shape[0]
+    adv = np.zeros_like(rew); last = 0
+    for t in reversed(range(T)):
+        if t == T - 1:
+            nnt, nv = 1.0 - last_done, last_val
+        else:
+            nnt, nv = 1.0 - dones[t + 1], val[t + 1]
+        delta = rew[t] + gamma * nv * nnt - val[t]
+        adv[t] = last = delta + gamma * lam * nnt * last
+    return adv + val
+
+
+def test_gae_sf01_and_nstep_returns_match_the_runner_formulas():
+    rng = np.random.RandomState(0)
+    T, N = 17, 6
+    rew, val = rng.randn(T, N).astype(np.float32), rng.randn(T, N).astype(np.float32)
+    dones = (rng.rand(T, N) < 0.2).astype(np.float32)
+    lv, ld = rng.randn(N).astype(np.float32), (rng.rand(N) < 0.3).astype(np.float32)
+    ret, adv = rollout.gae(*(torch.from_numpy(x) for x in (rew, val, dones, lv, ld)), 0.99, 0.95)
+    assert np.allclose(ret.numpy(), _np_gae(rew, val, dones, lv, ld, 0.99, 0.95), atol=1e-5)
+    x = torch.arange(T * N * 3).reshape(T, N, 3)
+    f = rollout.sf01(x)
+    assert f.shape == (T * N, 3) and torch.equal(f[1], x[1, 0]) and torch.equal(f[T], x[0, 1])
+    # a2c n-step returns: per env, discount_with_dones(rewards + [value], dones + [0])[:-1] when the last step is not terminal
+    out = rollout.discount_with_dones(torch.from_numpy(rew), torch.from_numpy(dones), 0.9, bootstrap=torch.from_numpy(lv)).numpy()
+    for n in range(N):
+        r = 0.0 if dones[-1, n] else lv[n]
+        want = np.zeros(T, np.float32)
+        for t in reversed(range(T)):
+            r = rew[t, n] + 0.9 * r * (1.0 - dones[t, n])
+            want[t] = r
+        assert np.allclose(out[:, n], want, atol=1e-5)
+
+
+def test_policy_shapes_on_cpu():
+    pol = rollout.MlpPolicy(18, 4)
+    a, v, nl = pol.step(torch.rand(5, 18))
+    assert a.shape == (5,) and a.dtype == torch.int32 and v.shape == (5,) and nl.shape == (5,) and (nl > 0).all()
+    pc = rollout.MlpPolicy(18, continuous=True)
+    a, v, nl = pc.step(torch.rand(5, 18))
+    assert a.shape == (5, 2) and a.abs().max() <= 1.0
+    assert sum(p.numel() for p in pol.body.parameters()) == 18 * 256 + 256 + 2 * (256 * 256 + 256)
+
+
+def test_spaces_and_bounds():
+    low, high = highway_obs_bounds(4, np.float32)
+    assert low.shape == (18,) and low.dtype == np.float32
+    assert low.tolist() == [-5, -30, 0, 0] + [-60, -8] * 3 + [-20, -20] * 4
+    assert high.tolist() == [5, 30, 1200, 8] + [60, 8] * 3 + [20, 20] * 4
+    low8, _ = highway_obs_bounds(8)
+    assert low8.shape == (34,) and low8.dtype == np.float64
+    b = Box(low, high, dtype=np.float32)
+    assert b.shape == (18,) and b.contains(b.sample()) and Discrete(4).contains(3) and not Discrete(4).contains(4)
+
+
+def test_run_time_table_accumulates_like_the_reference():
+    from gym_highway_b200 import _lib
+    from gym_highway_b200.vec_env import _run_time_table
+    tab = _run_time_table(_lib.sim_params(False))
+    assert tab[9] == 0.25000000000000006 and tab[2160] == 60.00000000000145 and tab[2159] < 60.0
+
+
+def test_make_vec_env_rejects_unknown_ids():
+    from gym_highway_b200 import ENV_IDS
+    from gym_highway_b200.cmd_util import make_vec_env
+    assert ENV_IDS['Highway-v0'] == ('sa', False) and ENV_IDS['MA-Highway-cont-train-v0'] == ('ma', True)
+    with pytest.raises(KeyError):
+        make_vec_env('CartPole-v0')

@@ -120,3 +120,18 @@ def test_ma_host_step_matches_device_step():
         o1, r1, d1, _ = a.step(torch.from_numpy(act).cuda())
         o2, r2, d2 = b.step_host(act)
         assert bits_equal(o1.cpu().numpy(), o2) and bits_equal(r1.cpu().numpy(), r2) and np.array_equal(d1.cpu().numpy(), d2)
+
+
+def test_ma_gym_per_env_api():
+    from gym_highway_b200 import MultiAgentEnv, MultiAgentEnvContinuous
+    kw = {'manual': False, 'inf_obs': True, 'save': False, 'render': False, 'real_time': False}
+    env = MultiAgentEnv(world_config=kw, num_agents=5)
+    ob = env.reset()
+    assert len(ob) == 5 and ob[0].shape == (34,)
+    ob, r, d, info = env.step(np.eye(4)[[2, 2, 0, 1, 3]])
+    want = [-0.9982638888888888, -0.9982638888888888, -1.0, -1.0, -0.9986111111111111]  # reference probe, build container
+    assert np.allclose(r, want, atol=1e-6) and d == [False] * 5 and len(info['n']) == 5
+    envc = MultiAgentEnvContinuous(world_config=kw, num_agents=3)
+    envc.reset()
+    ob, r, d, info = envc.step([[0.1, 0.0]] * 3)
+    assert len(ob) == 3 and ob[0].shape == (26,)

@@ -172,3 +172,27 @@ def test_rollout_random_is_deterministic_and_sane():
     assert bits_equal(oa.cpu().numpy(), ob.cpu().numpy())
     o = oa.cpu().numpy()
     assert np.isfinite(o).all() and o.min() >= 0.0 and o.max() <= 1.0
+
+
+def test_gym_per_env_api_matches_reference_anchor():
+    """HighwayEnv (N=1 gym API): the survey's seed-0 anchor of the reference"""
+    from gym_highway_b200 import HighwayEnv, HighwayEnvContinuous, make_vec_env
+    env = HighwayEnv(manual=False, inf_obs=True, save=False, render=False, real_time=False)
+    ob = env.reset()
+    want = np.array([0.5, 0.5, 0.0166667, 0.46875, 0.1666667, 0.34375, 0.125, 0.5, 0.0, 0.65625, 0.5, 0.5,
+                     0.675, 0.5, 0.625, 0.5, 0.65, 0.5], np.float32)
+    assert ob.shape == (18,) and ob.dtype == np.float32 and np.allclose(ob, want, atol=1e-6)
+    rews = []
+    for a in [2, 2, 2, 0, 3, 1]:
+        ob, r, d, info = env.step(a)
+        rews.append(r)
+        assert d is False and set(info) == {"run_time", "num_obs_collisions", "num_agent_collisions"}
+    assert rews == [-0.998, -0.993, -0.985, -0.974, -0.912, -0.849]
+    envc = HighwayEnvContinuous(render=False)
+    envc.reset()
+    ob, r, d, info = envc.step([0.5, -0.25])
+    assert ob.shape == (18,) and isinstance(r, float)
+    v = make_vec_env('Highway-cont-train-v0', num_env=3, seed=1)
+    assert v.num_envs == 3 and v.continuous
+    with pytest.raises(NotImplementedError):
+        HighwayEnv(render=True)
