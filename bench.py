@@ -9,7 +9,8 @@ observation, reward, done, auto-reset) = ONE kernel launch.  Prints ONE JSON lin
 
 Timing: CUDA events on the launching stream around every step launch; the L2 (126 MB) is flushed
 between timed launches by overwriting a 256 MiB buffer (outside the event pairs) unless the batch's
-working set is itself larger than L2 (--envs >= 2M), so every launch reads its state from HBM.
+working set is itself larger than L2 (the default: 4,194,304 single-agent envs per GPU move 1.1 GB per
+launch), so every launch reads its state from HBM.
 """
 import argparse
 import json
@@ -88,9 +89,10 @@ class ClockSampler(threading.Thread):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--envs", type=int, default=65536, help="environments PER GPU (weak scaling)")
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--envs", type=int, default=0, help="environments PER GPU (weak scaling); 0 = 4,194,304 (SA) / 262,144 (MA)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[1] side measurement")
     ap.add_argument("--workload", default="sa_discrete")
     ap.add_argument("--agents", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -113,7 +115,7 @@ def workload_info(args):
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_arm(args, info, steps_hint=0, nthreads=None):
+def cpu_arm(args, info, steps_hint=0, nthreads=None, warmup=3):
     """time the C restatement of the reference step on the host cores: bounded sample of the workload"""
     from oracle import oracle as orc
     nthreads = nthreads or os.cpu_count() or 1
@@ -139,10 +141,11 @@ def cpu_arm(args, info, steps_hint=0, nthreads=None):
             t0 = time.perf_counter()
             mo.ma_step(st, act, continuous=info["continuous"], seed=0, quantise=True, nthreads=nthreads)
             return time.perf_counter() - t0
-    for _ in range(3):
+    for _ in range(max(3, warmup)):
         one_step()
     probe = one_step()
-    steps = steps_hint or int(max(10, min(2000, 12.0 / max(probe, 1e-6))))
+    # bounded: about 12 s of CPU work unless the caller names a step count, and never more than ~60 s
+    steps = int(max(10, min(2000, 12.0 / max(probe, 1e-6)))) if not steps_hint else int(max(1, min(steps_hint, 60.0 / max(probe, 1e-6))))
     total = sum(one_step() for _ in range(steps))
     return dict(value=n * steps / total, unit="env-steps/s", cores=nthreads, kind="port",
                 sample="%d envs x %d steps of the C restatement (oracle/*.c, fp64, pthreads), action generation excluded; "
@@ -155,21 +158,86 @@ def reference_main(args, info):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = args.steps if args.cpu_steps == 0 else args.cpu_steps
-    # keep the whole run within a few minutes whatever --steps says
-    base = cpu_arm(args, info, steps_hint=0)
+    # each "step" of this arm is one env.step of a bounded 65,536-env sample of the workload on all host cores
+    base = cpu_arm(args, info, steps_hint=args.cpu_steps or args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": "env-steps/s", "value": base["value"], "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": base["steps"], "warmup": 3, "ms_per_step": base["ms_per_step"],
+            "n_gpus": args.gpus, "steps": base["steps"], "warmup": max(3, args.warmup), "ms_per_step": base["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": info["name"], "envs_per_step_sample": base["envs"], "requested_steps": steps},
+            "config": {"workload": info["name"], "envs_per_step_sample": base["envs"], "requested_steps": args.steps},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def make_env(info, args, n, dev, rank):
+    if info["kind"] == "sa":
+        from gym_highway_b200 import HighwayVecEnv
+        return HighwayVecEnv(n, continuous=info["continuous"], seed=0, device=dev, env_id0=rank * n), 1
+    from gym_highway_b200 import HighwayMAVecEnv
+    return HighwayMAVecEnv(n, num_agents=args.agents, continuous=info["continuous"], seed=0, device=dev, env_id0=rank * n), args.agents
+
+
+def make_actions(info, n, A, dev, rank, ring=8):
+    """synthetic actions, i.i.d. uniform, generated on device: a ring of `ring` per-step buffers"""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    if info["continuous"]:
+        shape = (ring, n, 2) if info["kind"] == "sa" else (ring, n, A, 2)
+        return torch.rand(shape, generator=g, device=dev) * 2 - 1
+    shape = (ring, n) if info["kind"] == "sa" else (ring, n, A)
+    return torch.randint(0, 4, shape, generator=g, device=dev, dtype=torch.int32)
+
+
+def timed_steps(env, acts, steps, warmup, flush_buf, world, dev, sampler=None):
+    """W untimed + K timed env.step launches; CUDA events around every launch on the launching stream;
+    returns per-launch device times [ms] and the wall time of the timed region"""
+    import torch
+    import torch.distributed as dist
+    ring = acts.shape[0]
+    if hasattr(env, "rollout_random"):
+        env.rollout_random(150, action_ctr0=0)  # decorrelate the batch: episodes at different phases
+    for w in range(max(warmup, 3)):
+        env.step_async(acts[w % ring]); env.step_wait()
+    torch.cuda.synchronize(dev)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    if sampler is not None:
+        sampler.start()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        if flush_buf is not None:
+            flush_buf.fill_(k & 0xFF)
+        starts[k].record()
+        env.step_async(acts[k % ring])
+        ends[k].record()
+        env.step_wait()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    return np.array([s.elapsed_time(e) for s, e in zip(starts, ends)]), wall
+
+
+def ncu_traffic(kind, continuous, n):
+    """DRAM bytes per launch of the step kernel from the committed ncu --set full capture, if one exists for this size"""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return tab.get("%s_%s_%d" % (kind, "continuous" if continuous else "discrete", n))
+    except Exception:
+        return None
+
+
 def main():
     args = parse()
+    if args.envs <= 0:
+        # SA: a point of the scaling sweep (BASELINE.json configs[4]) whose working set (1.1 GB/step) is far larger than
+        # L2, so launches are HBM-fed without flushing; configs[1] (65,536 envs) is reported alongside under "configs1".
+        args.envs = 4194304 if args.workload.startswith("sa_") else 262144
     info = workload_info(args)
     if args.impl == "reference":
         return reference_main(args, info)
@@ -185,57 +253,15 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.envs
-    if info["kind"] == "sa":
-        from gym_highway_b200 import HighwayVecEnv
-        env = HighwayVecEnv(n, continuous=info["continuous"], seed=0, device=dev, env_id0=rank * n)
-        A = 1
-    else:
-        from gym_highway_b200 import HighwayMAVecEnv
-        A = args.agents
-        env = HighwayMAVecEnv(n, num_agents=A, continuous=info["continuous"], seed=0, device=dev, env_id0=rank * n)
-
-    # synthetic actions, i.i.d. uniform, generated on device, one buffer per step of a ring
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    ring = 8
-    if info["continuous"]:
-        shape = (ring, n, 2) if info["kind"] == "sa" else (ring, n, A, 2)
-        acts = torch.rand(shape, generator=g, device=dev) * 2 - 1
-    else:
-        shape = (ring, n) if info["kind"] == "sa" else (ring, n, A)
-        acts = torch.randint(0, 4, shape, generator=g, device=dev, dtype=torch.int32)
-
+    env, A = make_env(info, args, n, dev, rank)
+    acts = make_actions(info, n, A, dev, rank)
     working_set = n * info["bytes_per_step"]
     flush = (not args.no_flush) and working_set < 2 * L2_BYTES
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if flush else None
 
-    # decorrelate the batch first: a few hundred steps so that episodes are at different phases
-    env.rollout_random(150, action_ctr0=0) if hasattr(env, "rollout_random") else None
-    for w in range(max(args.warmup, 3)):
-        env.step_async(acts[w % ring]); env.step_wait()
-    torch.cuda.synchronize(dev)
-
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    sampler.start()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        if flush:
-            flush_buf.fill_(k & 0xFF)
-        starts[k].record()
-        env.step_async(acts[k % ring])
-        ends[k].record()
-        env.step_wait()
-    torch.cuda.synchronize(dev)
-    t_wall = time.perf_counter() - t_wall0
+    dev_ms, t_wall = timed_steps(env, acts, args.steps, args.warmup, flush_buf, world, dev, sampler)
     clocks = sampler.result()
-    if world > 1:
-        dist.barrier()
-    dev_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
     total_ms = float(dev_ms.sum())
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -244,53 +270,76 @@ def main():
     value = world * n * args.steps / (total_ms * 1e-3)
 
     # end to end through the host-buffer C-ABI call: pinned host actions in, host obs/rew/done out
-    e2e = None
-    if hasattr(env, "step_host"):
-        h_acts = acts.cpu().numpy()
-        e2e_steps = max(10, min(args.steps, 100))
-        for w in range(3):
-            env.step_host(h_acts[w % ring])
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for k in range(e2e_steps):
-            env.step_host(h_acts[k % ring])
-        torch.cuda.synchronize(dev)
-        t_e2e = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e = float(t.item())
-        act_bytes = int(h_acts[0].nbytes)
-        out_bytes = n * A * (4 * A + 14 if info["kind"] == "ma" else 18) * 4 + n * A * 4 + n * A
-        e2e = {"value": world * n * e2e_steps / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
-               "d2h_bytes_per_step": out_bytes, "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
-               "api": ("HighwayVecEnv.step_host -> hw_sa_step_host" if info["kind"] == "sa" else "HighwayMAVecEnv.step_host -> hw_ma_step_host")
-                      + " (C ABI, host buffers, copies + stream drain inside)"}
+    h_acts = acts.cpu().numpy()
+    ring = h_acts.shape[0]
+    e2e_steps = max(5, min(args.steps, 50))
+    for w in range(3):
+        env.step_host(h_acts[w % ring])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        env.step_host(h_acts[k % ring])
+    torch.cuda.synchronize(dev)
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    act_bytes = int(h_acts[0].nbytes)
+    out_bytes = n * A * (4 * A + 14 if info["kind"] == "ma" else 18) * 4 + n * A * 4 + n * A
+    e2e = {"value": world * n * e2e_steps / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
+           "d2h_bytes_per_step": out_bytes, "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
+           "api": ("HighwayVecEnv.step_host -> hw_sa_step_host" if info["kind"] == "sa" else "HighwayMAVecEnv.step_host -> hw_ma_step_host")
+                  + " (C ABI, host buffers: pinned-host actions H2D, kernel, obs/rew/done D2H, stream drain, all inside the call)"}
+    stats = env.episode_statistics()
+    live = None
+    if info["kind"] == "ma":
+        live = float(((env.head[0].view(torch.int32) >> 20) & 31).float().mean().item())
+    del env, acts
+    torch.cuda.empty_cache()
 
-    stats = env.episode_statistics() if hasattr(env, "episode_statistics") else {}
+    # BASELINE.json configs[1]: 65,536 single-agent envs on one GPU (0.7 waves: latency-bound), L2 flushed between launches
+    configs1 = None
+    if info["kind"] == "sa" and rank == 0 and n != 65536 and not args.no_extras:
+        fb = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        e1, _ = make_env(info, args, 65536, dev, rank)
+        a1 = make_actions(info, 65536, 1, dev, rank)
+        ms1, _ = timed_steps(e1, a1, 200, 10, fb, 1, dev)
+        configs1 = {"workload": "configs[1]: 65,536 envs on 1 GPU, L2 flushed between launches", "env_steps_per_s": 65536 / (float(ms1.mean()) * 1e-3),
+                    "avg_launch_us": float(ms1.mean()) * 1e3, "roofline_frac": 65536 * info["bytes_per_step"] / (float(ms1.mean()) * 1e-3) / 1e9 / measured_peak()[0]}
+        del e1, a1, fb
+        torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = measured_peak()
         avg_launch_s = float(dev_ms.mean()) * 1e-3
-        achieved = n * info["bytes_per_step"] / avg_launch_s / 1e9
+        bps = info["bytes_per_step"]
+        if live is not None:  # only the live obstacle slots are read and written
+            bps = 2 * (36 * A + 16 * live + 40) + 4 * A + 4 * A * (4 * A + 14) + 4 * A + A
+        achieved = n * bps / avg_launch_s / 1e9
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": info["dtype"], "data": "synthetic",
             "config": {"workload": info["name"], "envs_per_gpu": n, "ticks_per_step": 9,
                        "l2": "flushed between timed launches (256 MiB overwrite outside the event pairs)" if flush
-                             else "working set larger than L2, no flush",
+                             else "inputs larger than L2 (%.0f MB per launch vs 126 MB), no flush" % (working_set / 1e6),
                        "parallelism": "independent env shards, %d rank(s), no data-path collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "sa_step_kernel" if info["kind"] == "sa" else "ma_step_kernel",
-                         "algorithmic_bytes_per_env_step": info["bytes_per_step"],
+                         "traffic": ncu_traffic(info["kind"], info["continuous"], n), "peak_source": peak_src,
+                         "kernel": "sa_step_kernel" if info["kind"] == "sa" else "ma_step_kernel",
+                         "algorithmic_bytes_per_env_step": bps,
                          "avg_launch_us": avg_launch_s * 1e6, "min_launch_us": float(dev_ms.min()) * 1e3},
             "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
-            "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
-            "episodes": stats,
+            "wall_ms_per_step": 1e3 * t_wall / args.steps, "episodes": stats,
         }
+        if configs1:
+            line["configs1"] = configs1
+        if info["kind"] == "ma":
+            line["agent_steps_per_s"] = value * A
+            line["mean_live_obstacles"] = live
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_arm(args, info).items() if k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
