@@ -15,6 +15,7 @@ FLAG_CONTINUOUS = 1
 FLAG_NO_INF_OBS = 2
 FLAG_NO_AUTORESET = 4
 FLAG_SHARED_REWARD = 16
+FLAG_EXACT_STEERING = 32
 MA_MAX_AGENTS = 5
 MA_MAX_SLOTS = 16
 

@@ -94,7 +94,7 @@ __device__ __forceinline__ void ma_reset_env(MaHead &h, double *sm_car, double *
 }
 
 // one world.act() followed by Scenario.rewards(); rewards[a] is overwritten, done bits are or-ed into `done`
-template <bool CONT>
+template <bool CONT, bool EXACT>
 __device__ __forceinline__ void ma_tick(MaHead &h, double *sm_car, double *sm_ob, uint32_t *cbits, const int A, const int K,
                                         const MaConsts &C, const bool inf_obs, const int *act_d, const double *act_c,
                                         const uint64_t seed, const uint64_t env_id, double *rewards, uint32_t &done)
@@ -173,7 +173,7 @@ __device__ __forceinline__ void ma_tick(MaHead &h, double *sm_car, double *sm_ob
             }
         }
         double ang = 0.0;
-        if (steer != 0.0) ang = ddiv(vx, dmul(4.0, __drcp_rn(tan_small(dmul(steer, kDeg2Rad)))));  // 4/t == 4*(1/t) exactly
+        if (steer != 0.0) ang = angular_velocity<EXACT>(vx, steer);
         double vy = CAR(a, C_VY);
         if (!CONT) vy = ang;  // agent.py:144: velocity.y = angular_velocity (discrete update only)
         const double vdt = dmul(vx, dt);
@@ -381,7 +381,7 @@ __device__ __forceinline__ void ma_store(const MaHead &h, const double *sm_car, 
         S.obst[(int64_t)k * n + i] = make_float4((float)OB(k, O_PX), (float)OB(k, O_RX), (float)OB(k, O_VX), (float)OB(k, O_IV));
 }
 
-template <bool CONT>
+template <bool CONT, bool EXACT>
 __global__ void __launch_bounds__(kMaBlock)
 ma_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew,
                uint8_t *__restrict__ done_out, double *__restrict__ term, unsigned long long *__restrict__ stats,
@@ -419,7 +419,7 @@ ma_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict__ o
     for (int a = 0; a < kMaxA; ++a) r[a] = 0.0;
     uint32_t done = 0;
     for (int t = 0; t < C.ticks_per_step; ++t) {
-        ma_tick<CONT>(h, sm_car, sm_ob, cbits, A, K, C, inf_obs, act_d, act_c, seed, env_id0 + (uint64_t)i, r, done);
+        ma_tick<CONT, EXACT>(h, sm_car, sm_ob, cbits, A, K, C, inf_obs, act_d, act_c, seed, env_id0 + (uint64_t)i, r, done);
         if (done) break;  // highway_env.py:85-86
     }
     if (shared_reward) {  // highway_env.py:92-94: every agent receives np.sum(reward_n)
@@ -533,17 +533,18 @@ static int ma_launch_step(const HwMaState *st, const void *actions, const HwMaOu
     if (rc) return rc;
     if (!actions || !out || !out->obs || !out->rew || !out->done || !P) return HW_E_BADARG;
     if (P->ticks_per_step < 1 || P->timeout_tick < 1 || P->timeout_tick > 0xFFFF || !(P->dt > 0.0)) return HW_E_BADARG;
-    MaConsts C;
-    C.dt = P->dt; C.k30dt = 30.0 * P->dt; C.ticks_per_step = P->ticks_per_step; C.timeout_tick = P->timeout_tick;
+    MaConsts C_;
+    C_.dt = P->dt; C_.k30dt = 30.0 * P->dt; C_.ticks_per_step = P->ticks_per_step; C_.timeout_tick = P->timeout_tick;
     const size_t smem = ma_smem(st);
     const unsigned grid = (unsigned)((n + kMaBlock - 1) / kMaBlock);
-    if (flags & HW_FLAG_CONTINUOUS) {
-        if ((rc = ma_prepare(ma_step_kernel<true>, smem))) return rc;
-        ma_step_kernel<true><<<grid, kMaBlock, smem, stream>>>(ma_ptrs(st), actions, out->obs, out->rew, out->done, out->term, out->stats, C, seed, env_id0, n, flags);
-    } else {
-        if ((rc = ma_prepare(ma_step_kernel<false>, smem))) return rc;
-        ma_step_kernel<false><<<grid, kMaBlock, smem, stream>>>(ma_ptrs(st), actions, out->obs, out->rew, out->done, out->term, out->stats, C, seed, env_id0, n, flags);
-    }
+#define HW_MA_LAUNCH(C, E) do { \
+        if ((rc = ma_prepare(ma_step_kernel<C, E>, smem))) return rc; \
+        ma_step_kernel<C, E><<<grid, kMaBlock, smem, stream>>>(ma_ptrs(st), actions, out->obs, out->rew, out->done, out->term, out->stats, C_, seed, env_id0, n, flags); \
+    } while (0)
+    const bool exact = (flags & HW_FLAG_EXACT_STEERING) != 0;
+    if (flags & HW_FLAG_CONTINUOUS) { if (exact) HW_MA_LAUNCH(true, true); else HW_MA_LAUNCH(true, false); }
+    else                            { if (exact) HW_MA_LAUNCH(false, true); else HW_MA_LAUNCH(false, false); }
+#undef HW_MA_LAUNCH
     return (int)cudaGetLastError();
 }
 

@@ -82,9 +82,10 @@ __device__ __noinline__ int sa_collide_exact(double px, double py, double o0, do
 template <bool CONT>
 __device__ __forceinline__ double road_clamp(double y)
 {
+    // `if y < lo: y = lo  elif y > 6: y = min(y, 7)` == (y < lo) ? lo : min(y, 7): for lo <= y <= 6 the min is the identity
     const double lo = CONT ? 1.0 : 0.0;
-    const double hi = (7.0 < y) ? 7.0 : y;  // min(y, 7), only applied when y > 6
-    return (y < lo) ? lo : ((y > 6.0) ? hi : y);
+    const double top = (7.0 < y) ? 7.0 : y;
+    return (y < lo) ? lo : top;
 }
 
 // hi word of a double; for non-negative values the unsigned order of hi words is the numeric order
@@ -114,7 +115,7 @@ struct SaConsts {
 // evaluated with selects, and only genuinely rare events (an obstacle within a car length, a respawn) or
 // long ones (the steering path with its tan and two divisions) stay behind branches.  FIRST = first tick
 // of the step, the only one that can see the collision lock or a car that is not yet pinned at x = 10.
-template <bool CONT, bool FIRST>
+template <bool CONT, bool FIRST, bool EXACT>
 __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaConsts &K, const bool inf_obs,
                                        const uint32_t amask, const uint32_t apair, const double a0_5dt, const double a1_30dt,
                                        const uint64_t seed, const uint64_t env_id)
@@ -197,9 +198,7 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
     }
     const double vdt = dmul(e.vx, dt);
     if (e.steer != 0.0) {
-        // angular_velocity = vx / (length / tan(radians(steering))); 4/t == 4 * (1/t) exactly (power of two)
-        const double radius = dmul(4.0, __drcp_rn(tan_small(dmul(e.steer, kDeg2Rad))));
-        const double ang = ddiv(e.vx, radius);
+        const double ang = angular_velocity<EXACT>(e.vx, e.steer);
         // position += velocity * dt has velocity.y == 0: py + 0.0 == py for every py the clamps can produce
         if (CONT) e.py = dsub(e.py, dmul(ang, dt));
         else      e.py = dsub(e.py, dmul(dmul(dmul(ang, kRad2Deg), dt), dt));
@@ -309,7 +308,7 @@ __device__ __forceinline__ void store_obs_warp(float *sm_tile, float *__restrict
 #define HW_SA_MIN_BLOCKS_C 8
 #endif
 
-template <bool CONT, bool RANDOM_ACTIONS>
+template <bool CONT, bool RANDOM_ACTIONS, bool EXACT>
 __global__ void __launch_bounds__(kSaBlock, CONT ? HW_SA_MIN_BLOCKS_C : HW_SA_MIN_BLOCKS_D)
 sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew,
                uint8_t *__restrict__ done, int4 *__restrict__ term, unsigned long long *__restrict__ stats,
@@ -371,10 +370,10 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                 apair = (amask & (kBitLeft | kBitRight)) ? (kBitLeft | kBitRight) : (kBitDoAcc | kBitDoMaint);
             }
             // env.step: up to ticks_per_step ticks, stop at the first crash (highway_env.py:99-108)
-            int ncol = sa_tick<CONT, true>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
+            int ncol = sa_tick<CONT, true, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
             e.px = 10.0;  // the only car is always the leader (:212-213)
             for (int t = 1; t < K.ticks_per_step && ncol == 0; ++t)
-                ncol = sa_tick<CONT, false>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
+                ncol = sa_tick<CONT, false, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
             const uint32_t tick = e.bits & HW_BITS_TICK_MASK;
             const bool timeout = tick >= (uint32_t)K.timeout_tick;
             is_done = timeout || ncol > 0;
@@ -493,9 +492,12 @@ static int launch_step(const HwSaState *st, const void *actions, const HwSaOut *
     const unsigned grid = (unsigned)((n + kSaBlock - 1) / kSaBlock);
     int4 *term = reinterpret_cast<int4 *>(out->term);
     const bool cont = (flags & HW_FLAG_CONTINUOUS) != 0;
-#define HW_LAUNCH(C, R) sa_step_kernel<C, R><<<grid, kSaBlock, 0, stream>>>(S, actions, out->obs, out->rew, out->done, term, out->stats, K, seed, env_id0, action_ctr0, steps, n, flags)
-    if (cont) { if (random_actions) HW_LAUNCH(true, true); else HW_LAUNCH(true, false); }
-    else      { if (random_actions) HW_LAUNCH(false, true); else HW_LAUNCH(false, false); }
+    const bool exact = (flags & HW_FLAG_EXACT_STEERING) != 0;
+#define HW_LAUNCH(C, R, E) sa_step_kernel<C, R, E><<<grid, kSaBlock, 0, stream>>>(S, actions, out->obs, out->rew, out->done, term, out->stats, K, seed, env_id0, action_ctr0, steps, n, flags)
+#define HW_LAUNCH_E(C, R) do { if (exact) HW_LAUNCH(C, R, true); else HW_LAUNCH(C, R, false); } while (0)
+    if (cont) { if (random_actions) HW_LAUNCH_E(true, true); else HW_LAUNCH_E(true, false); }
+    else      { if (random_actions) HW_LAUNCH_E(false, true); else HW_LAUNCH_E(false, false); }
+#undef HW_LAUNCH_E
 #undef HW_LAUNCH
     return (int)cudaGetLastError();
 }

@@ -143,7 +143,8 @@ class HighwayVecEnv(VecEnv):
     """
 
     def __init__(self, num_envs, continuous=False, seed=0, device=None, manual=False, inf_obs=True, save=False,
-                 render=False, real_time=False, env_id0=0, return_numpy=False, auto_reset=True, track_stats=True):
+                 render=False, real_time=False, env_id0=0, return_numpy=False, auto_reset=True, track_stats=True,
+                 exact_steering=False):
         if manual or save or render:
             raise NotImplementedError("manual / save / render belong to the interactive pygame front-end")
         if num_envs < 1:
@@ -157,7 +158,8 @@ class HighwayVecEnv(VecEnv):
         self.params = _lib.sim_params(real_time)
         self.return_numpy = bool(return_numpy)
         self._flags = ((_lib.FLAG_CONTINUOUS if continuous else 0) | (0 if inf_obs else _lib.FLAG_NO_INF_OBS)
-                       | (0 if auto_reset else _lib.FLAG_NO_AUTORESET))
+                       | (0 if auto_reset else _lib.FLAG_NO_AUTORESET)
+                       | (_lib.FLAG_EXACT_STEERING if exact_steering else 0))
         self._seed = int(seed) & (2 ** 64 - 1)
         self._env_id0 = int(env_id0)
         low, high = highway_obs_bounds(4, np.float32)

@@ -41,6 +41,8 @@ extern "C" {
 #define HW_FLAG_NO_INF_OBS   2  /* inf_obs=False: obstacles are never respawned */
 #define HW_FLAG_NO_AUTORESET 4  /* leave terminal states in place (gym per-env semantics) */
 #define HW_FLAG_SHARED_REWARD 16 /* multi-agent: every car receives the sum of the rewards (shared_reward=True) */
+#define HW_FLAG_EXACT_STEERING 32 /* evaluate vx / (4 / tan) with the reference's two divisions instead of vx*tan/4
+                                    * (slower; floats then match the fp64 reference bit for bit after fp32 rounding) */
 
 /* discrete actions, gym_highway/envs/highway_env.py:14-20 */
 #define HW_ACT_LEFT 0

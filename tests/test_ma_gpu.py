@@ -48,7 +48,7 @@ def test_golden_transitions(name):
     A, K = int(g["num_agents"]), int(g["num_slots"])
     n = len(g["env_id"])
     env = _env(n, A, continuous=bool(g["continuous"]), seed=int(g["seed"]), env_id0=0, auto_reset=False,
-               shared_reward=bool(g["shared_reward"]), num_slots=K)
+               shared_reward=bool(g["shared_reward"]), num_slots=K, exact_steering=True)
     _load_state(env, ma_state_from_golden(g))
     obs, rew, done, _ = env.step(torch.from_numpy(np.ascontiguousarray(g["action"])).cuda())
     got = _read_state(env)
@@ -66,7 +66,7 @@ def test_golden_transitions(name):
 @pytest.mark.parametrize("A,continuous", [(5, False), (5, True), (3, False), (1, True)])
 def test_trajectory_parity(A, continuous):
     n, steps, seed = 2048, 400, 9
-    env = _env(n, A, continuous=continuous, seed=seed, env_id0=7)
+    env = _env(n, A, continuous=continuous, seed=seed, env_id0=7, exact_steering=True)
     st = mo.MaState(n, A)
     mo.ma_reset(st)
     rng = np.random.RandomState(2)
@@ -135,3 +135,30 @@ def test_ma_gym_per_env_api():
     envc.reset()
     ob, r, d, info = envc.step([[0.1, 0.0]] * 3)
     assert len(ob) == 3 and ob[0].shape == (26,)
+
+
+@pytest.mark.parametrize("A,continuous", [(5, False), (3, True)])
+def test_fast_mode_per_step_parity_from_identical_states(A, continuous):
+    """default steering term (vx*tan/4, one rounding): discrete state exact, floats within 1e-5 relative per step"""
+    n, steps, seed = 2048, 150, 4
+    env = _env(n, A, continuous=continuous, seed=seed, env_id0=1)
+    rng = np.random.RandomState(5)
+    nbits = nvals = 0
+    for t in range(steps):
+        st = _read_state(env)
+        if continuous:
+            act = rng.uniform(-1, 1, (n, A, 2)).astype(np.float32); act[:, :, 1] *= 0.1
+        else:
+            act = np.where(rng.rand(n, A) < 0.6, 2, rng.randint(0, 4, (n, A))).astype(np.int32)
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        want = mo.ma_step(st, act, continuous=continuous, seed=seed, env_id0=1, quantise=True, nthreads=8)
+        got = _read_state(env)
+        assert np.array_equal(done.cpu().numpy(), want["done"]), "done differs at step %d" % t
+        for f in ("lane", "cflags", "tick", "leader", "nobs", "olane", "ofresh", "newest", "nc_obs", "nc_agent", "spawn_ctr", "ep_len"):
+            assert np.array_equal(getattr(got, f), getattr(st, f)), "%s differs at step %d" % (f, t)
+        for a, b in ((got.car, st.car), (got.obst, st.obst), (obs.cpu().numpy(), want["obs"]), (rew.cpu().numpy(), want["rew"])):
+            a32, b32 = f32(a), f32(b)
+            rel = np.abs(a32.astype(np.float64) - b32) / np.maximum(np.abs(b32.astype(np.float64)), 1e-3)
+            assert rel.max() <= 1e-5
+            nbits += int(np.sum(a32.view(np.uint32) != b32.view(np.uint32))); nvals += a32.size
+    assert nbits <= 1e-5 * nvals, "%d of %d float values differ in the last bit" % (nbits, nvals)

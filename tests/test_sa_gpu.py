@@ -61,7 +61,7 @@ def test_golden_transitions(name):
     cont, rt, seed = bool(g["continuous"]), bool(g["real_time"]), int(g["seed"])
     n = len(g["out_done"])
     assert np.array_equal(g["env_id"], np.arange(n))  # transition i was recorded as environment i
-    env = _env(n, continuous=cont, real_time=rt, seed=seed, env_id0=0, auto_reset=False)
+    env = _env(n, continuous=cont, real_time=rt, seed=seed, env_id0=0, auto_reset=False, exact_steering=True)
     _load_state(env, sa_state_from_golden(g))
     obs, rew, done, _ = env.step(torch.from_numpy(np.ascontiguousarray(g["action"])).cuda())
     got = _read_state(env)
@@ -80,7 +80,7 @@ def test_golden_transitions(name):
 def test_trajectory_parity_1000_steps(continuous, real_time):
     """4096 envs x 1000 consecutive steps with auto-reset, kernel vs oracle on the same actions"""
     n, steps, seed = 4096, 1000, 5
-    env = _env(n, continuous=continuous, real_time=real_time, seed=seed, env_id0=100)
+    env = _env(n, continuous=continuous, real_time=real_time, seed=seed, env_id0=100, exact_steering=True)
     st = orc.SaState(n)
     orc.sa_reset(st)
     rng = np.random.RandomState(1)
@@ -113,7 +113,7 @@ def test_trajectory_parity_1000_steps(continuous, real_time):
 
 def test_tail_block_and_small_batches():
     for n in (1, 2, 31, 127, 129, 1000):
-        env = _env(n, seed=9)
+        env = _env(n, seed=9, exact_steering=True)
         st = orc.SaState(n); orc.sa_reset(st)
         rng = np.random.RandomState(n)
         for t in range(30):
@@ -196,3 +196,59 @@ def test_gym_per_env_api_matches_reference_anchor():
     assert v.num_envs == 3 and v.continuous
     with pytest.raises(NotImplementedError):
         HighwayEnv(render=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Default (fast) steering term: vx*tan/4 with one rounding instead of the reference's two divisions.  Parity
+# bar of the contract: discrete state bit-exact, floats within 1e-5 relative per step from identical states.
+def _float_report(name, got, want, max_bitdiff_frac):
+    got, want = f32(got), f32(want)
+    rel = np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want.astype(np.float64)), 1e-3)
+    assert rel.max() <= REL_TOL, "%s: max rel err %.3g" % (name, rel.max())
+    frac = float(np.mean(got.view(np.uint32) != want.view(np.uint32)))
+    assert frac <= max_bitdiff_frac, "%s: %.3g of the values differ in the last bit" % (name, frac)
+    return frac
+
+
+@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime"])
+def test_fast_mode_golden_transitions(name):
+    g = load_golden(name)
+    n = len(g["out_done"])
+    env = _env(n, continuous=bool(g["continuous"]), real_time=bool(g["real_time"]), seed=int(g["seed"]), env_id0=0,
+               auto_reset=False)
+    _load_state(env, sa_state_from_golden(g))
+    obs, rew, done, _ = env.step(torch.from_numpy(np.ascontiguousarray(g["action"])).cuda())
+    got = _read_state(env)
+    assert np.array_equal(got.lane, g["out_lft"][:, 0]) and np.array_equal(got.flags, g["out_lft"][:, 1])
+    assert np.array_equal(got.tick, g["out_lft"][:, 2]) and np.array_equal(got.ncoll, g["out_ncoll"])
+    assert np.array_equal(got.spawn_ctr, g["out_spawn_ctr"].astype(np.uint32))
+    assert np.array_equal(done.cpu().numpy(), g["out_done"])
+    _float_report(name + " car", got.car, g["out_car"], 1e-4)
+    _float_report(name + " obst", got.obst, g["out_obst"], 0.0)
+    _float_report(name + " obs", obs.cpu().numpy(), g["out_obs"], 1e-4)
+    _float_report(name + " rew", rew.cpu().numpy(), g["out_rew"], 0.0)
+
+
+@pytest.mark.parametrize("continuous", [False, True])
+def test_fast_mode_per_step_parity_from_identical_states(continuous):
+    """the contract literally: every step starts from the kernel's own (identical) state in the oracle"""
+    n, steps, seed = 4096, 300, 11
+    env = _env(n, continuous=continuous, seed=seed, env_id0=5)
+    rng = np.random.RandomState(3)
+    nbits = nvals = 0
+    for t in range(steps):
+        st = _read_state(env)
+        act = rng.uniform(-1, 1, (n, 2)).astype(np.float32) if continuous else rng.randint(0, 4, n).astype(np.int32)
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        want = orc.sa_step(st, act, continuous=continuous, seed=seed, env_id0=5, quantise=True, nthreads=8)
+        got = _read_state(env)
+        assert np.array_equal(done.cpu().numpy(), want["done"]), "done differs at step %d" % t
+        for f in ("lane", "flags", "tick", "ncoll", "spawn_ctr", "ep_len", "ep_ret_milli"):
+            assert np.array_equal(getattr(got, f), getattr(st, f)), "%s differs at step %d" % (f, t)
+        assert bits_equal(rew.cpu().numpy(), f32(want["rew"]))
+        for a, b in ((got.car, st.car), (got.obst, st.obst), (obs.cpu().numpy(), want["obs"])):
+            a32, b32 = f32(a), f32(b)
+            rel = np.abs(a32.astype(np.float64) - b32) / np.maximum(np.abs(b32.astype(np.float64)), 1e-3)
+            assert rel.max() <= REL_TOL
+            nbits += int(np.sum(a32.view(np.uint32) != b32.view(np.uint32))); nvals += a32.size
+    assert nbits <= 1e-6 * nvals, "%d of %d float values differ in the last bit" % (nbits, nvals)
