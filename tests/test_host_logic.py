@@ -135,3 +135,76 @@ def test_make_vec_env_rejects_unknown_ids():
     assert ENV_IDS['Highway-v0'] == ('sa', False) and ENV_IDS['MA-Highway-cont-train-v0'] == ('ma', True)
     with pytest.raises(KeyError):
         make_vec_env('CartPole-v0')
+
+
+class _FakeInfos(object):
+    def __init__(self, eps):
+        self._eps = eps
+
+    def episodes(self):
+        return self._eps
+
+
+class _FakeVenv(object):
+    num_envs = 4
+
+    def __init__(self):
+        self.t = 0
+
+    def reset(self):
+        return "obs0"
+
+    def step_async(self, a):
+        self.t += 1
+
+    def step_wait(self):
+        eps = [dict(env=1, r=-12.345678, l=7, t=0.0)] if self.t % 2 == 0 else []
+        return "obs", "rew", "done", _FakeInfos(eps)
+
+    def close(self):
+        pass
+
+
+def test_monitor_file_format(tmp_path):
+    from gym_highway_b200.monitor import VecMonitor, load_results
+    path = str(tmp_path / "run0")
+    m = VecMonitor(_FakeVenv(), filename=path, env_id="Highway-v0")
+    assert m.reset() == "obs0"
+    for _ in range(6):
+        m.step([0, 0, 0, 0])
+    m.close()
+    lines = open(path + ".monitor.csv").read().splitlines()
+    assert lines[0].startswith('# {') and '"env_id": "Highway-v0"' in lines[0] and lines[1] == "r,l,t"
+    header, rows = load_results(path + ".monitor.csv")
+    assert len(rows) == 3 and rows[0]["r"] == -12.345678 and rows[0]["l"] == 7 and header["env_id"] == "Highway-v0"
+    assert m.get_total_steps() == 24 and m.means() == (-12.345678, 7.0) and m.get_episode_lengths() == [7, 7, 7]
+
+
+def test_ring_memory_matches_sequential_appends():
+    from gym_highway_b200.replay import RingMemory, RunningMeanStd
+    A, od, ad, limit = 3, 5, 2, 10
+    mem = RingMemory(limit, A, od, ad)
+    ref = []  # what a python list capped at `limit` would hold
+    g = torch.Generator().manual_seed(0)
+    for it in range(5):
+        n = 4
+        o0, o1 = torch.rand(n, A, od, generator=g), torch.rand(n, A, od, generator=g)
+        a, r, d = torch.rand(n, A, ad, generator=g), torch.rand(n, A, generator=g), (torch.rand(n, A, generator=g) < 0.3).float()
+        mem.append(o0, a, r, o1, d)
+        for i in range(n):
+            ref.append((o0[i], a[i], r[i], o1[i], d[i]))
+        ref = ref[-limit:]
+        assert mem.nb_entries == len(ref)
+        for i in (0, len(ref) // 2, len(ref) - 1):
+            e = mem.get(i)
+            assert torch.equal(e["obs0"], ref[i][0]) and torch.equal(e["actions"], ref[i][1]) and torch.equal(e["obs1"], ref[i][3])
+            assert torch.equal(e["rewards"][:, 0], ref[i][2]) and torch.equal(e["terminals1"][:, 0], ref[i][4])
+    b = mem.sample(6, generator=g)
+    assert b["obs0"].shape == (6, A, od) and b["rewards"].shape == (6, A, 1)
+    with pytest.raises(KeyError):
+        mem.get(limit)
+    rms = RunningMeanStd(shape=(od,), epsilon=0.0)
+    x = torch.randn(50, od, generator=g).double()
+    rms.update(x[:20]); rms.update(x[20:])
+    assert torch.allclose(rms.mean.double(), x.mean(0), atol=1e-6)
+    assert torch.allclose(rms.std.double(), x.std(0, unbiased=False).clamp(min=0.1), atol=1e-6)

@@ -32,3 +32,20 @@ def test_runner_collects_a_full_episode_on_device():
     for t in range(5):
         ob, _, _, _ = env2.step(a[:, t].contiguous())
         assert torch.equal(ob, o[:, t + 1, :])
+
+
+def test_vec_monitor_on_the_real_env(tmp_path):
+    from gym_highway_b200 import HighwayVecEnv
+    from gym_highway_b200.monitor import VecMonitor, load_results
+    env = VecMonitor(HighwayVecEnv(64, seed=3), filename=str(tmp_path / "m"), env_id="Highway-train-v0")
+    env.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for t in range(250):
+        env.step(torch.randint(0, 4, (64,), generator=g, device="cuda", dtype=torch.int32))
+    env.close()
+    header, rows = load_results(str(tmp_path / "m.monitor.csv"))
+    assert header["env_id"] == "Highway-train-v0" and len(rows) >= 64
+    assert all(1 <= r["l"] <= 240 for r in rows) and any(r["l"] == 240 for r in rows)
+    # a time-out episode of random actions has return in (-240, 0]; a crash adds -250 per hit obstacle
+    assert all(r["r"] <= 0 for r in rows)
+    assert len(env.get_episode_rewards()) == len(rows)
