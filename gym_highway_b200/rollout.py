@@ -14,8 +14,9 @@ import torch.nn as nn
 class MlpPolicy(nn.Module):
     """18 -> 256 -> 256 -> 256 -> (4 logits | 2 means, 1 value)"""
 
-    def __init__(self, obs_dim=18, n_actions=4, hidden=256, layers=3, continuous=False):
+    def __init__(self, obs_dim=18, n_actions=4, hidden=256, layers=3, continuous=False, bf16_inference=False):
         super().__init__()
+        self.bf16_inference = bf16_inference  # rollout-time forward in bf16 autocast (tensor cores); heads read out in fp32
         mods, d = [], obs_dim
         for _ in range(layers):
             mods += [nn.Linear(d, hidden), nn.ReLU()]
@@ -28,6 +29,10 @@ class MlpPolicy(nn.Module):
             self.logstd = nn.Parameter(torch.zeros(2))
 
     def forward(self, obs):
+        if self.bf16_inference and obs.is_cuda and not torch.is_grad_enabled():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                h = self.body(obs)
+                return self.pi(h).float(), self.vf(h).float().squeeze(-1)
         h = self.body(obs)
         return self.pi(h), self.vf(h).squeeze(-1)
 
@@ -41,8 +46,10 @@ class MlpPolicy(nn.Module):
             neglogp = (0.5 * (((a - out) / std) ** 2).sum(-1) + 0.5 * 1.8378770664093453 * a.shape[-1] + self.logstd.sum())
             return a.clamp(-1, 1), v, neglogp
         logp = torch.log_softmax(out, dim=-1)
-        a = torch.multinomial(logp.exp(), 1, generator=generator).squeeze(-1)
-        return a.to(torch.int32), v, -logp.gather(-1, a.unsqueeze(-1).long()).squeeze(-1)
+        # categorical sample by inverse CDF on one uniform per env (cheaper than torch.multinomial at 10^5..10^6 rows)
+        u = torch.rand(out.shape[0], 1, device=out.device, generator=generator)
+        a = (logp.exp().cumsum(-1) < u).sum(-1).clamp_(max=out.shape[-1] - 1)
+        return a.to(torch.int32), v, -logp.gather(-1, a.unsqueeze(-1)).squeeze(-1)
 
     @torch.no_grad()
     def value(self, obs):

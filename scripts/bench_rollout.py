@@ -25,7 +25,7 @@ from gym_highway_b200 import HighwayVecEnv
 from gym_highway_b200.rollout import MlpPolicy, Runner
 torch.manual_seed(0)
 env = HighwayVecEnv(args.envs, seed=0, device=dev, env_id0=rank * args.envs)
-pol = MlpPolicy(18, 4).to(dev)
+pol = MlpPolicy(18, 4, bf16_inference=True).to(dev)
 g = torch.Generator(device=dev); g.manual_seed(rank)
 run = Runner(env, pol, nsteps=args.nsteps, gamma=0.99, lam=0.95, generator=g)
 run.run(want_epinfos=False)  # warm-up rollout
