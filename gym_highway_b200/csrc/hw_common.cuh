@@ -66,7 +66,7 @@ constexpr uint32_t kSpawnTag = 0x48574159u;   // "HWAY": obstacle respawn stream
 constexpr uint32_t kActionTag = 0x41435421u;  // "ACT!": in-kernel random-action stream
 
 // out of line on purpose: a respawn is rare, and the ten Philox rounds would otherwise sit in the tick loop
-__device__ __noinline__ double2 spawn_uniform_pair(uint64_t seed, uint64_t env_id, uint32_t spawn_ctr)
+static __device__ __noinline__ double2 spawn_uniform_pair(uint64_t seed, uint64_t env_id, uint32_t spawn_ctr)
 {
     const uint4 w = philox4x32_10(make_uint4(spawn_ctr, (uint32_t)env_id, (uint32_t)(env_id >> 32), kSpawnTag),
                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
@@ -152,6 +152,16 @@ __device__ __forceinline__ double angular_velocity(double vx, double steer_deg)
     const double t = tan_small(dmul(steer_deg, kDeg2Rad));
     if (EXACT) return ddiv(vx, dmul(4.0, __drcp_rn(t)));
     return dmul(dmul(vx, t), 0.25);
+}
+
+// Sum over the 32 lanes of a fully converged warp.  Episode counters are accumulated per thread and
+// published with ONE atomic per warp and counter: when a whole batch times out on the same step (every env that
+// never crashed started together), per-thread atomics on eight addresses serialise into milliseconds.
+__device__ __forceinline__ long long warp_sum(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
 }  // namespace hw

@@ -382,16 +382,11 @@ __device__ __forceinline__ void ma_store(const MaHead &h, const double *sm_car, 
 }
 
 template <bool CONT, bool EXACT>
-__global__ void __launch_bounds__(kMaBlock)
-ma_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew,
-               uint8_t *__restrict__ done_out, double *__restrict__ term, unsigned long long *__restrict__ stats,
-               const MaConsts C, const uint64_t seed, const uint64_t env_id0, const int64_t n, const int flags)
+__device__ __forceinline__ void ma_step_env(const MaPtrs &S, double *sm_car, double *sm_ob, const void *__restrict__ actions,
+                                            float *__restrict__ obs, float *__restrict__ rew, uint8_t *__restrict__ done_out,
+                                            double *__restrict__ term, const MaConsts &C, const uint64_t seed, const uint64_t env_id0,
+                                            const int64_t n, const int flags, const int64_t i, long long *acc)
 {
-    extern __shared__ double sm_dyn[];
-    double *sm_car = sm_dyn;                                   // [A][C_NF][kMaBlock]
-    double *sm_ob = sm_dyn + (size_t)S.A * C_NF * kMaBlock;    // [K][O_NF][kMaBlock]
-    const int64_t i = (int64_t)blockIdx.x * kMaBlock + threadIdx.x;
-    if (i >= n) return;
     const int A = S.A, K = S.K, D = 4 * A + 14;
     const bool inf_obs = !(flags & HW_FLAG_NO_INF_OBS);
     const bool autoreset = !(flags & HW_FLAG_NO_AUTORESET);
@@ -443,15 +438,8 @@ ma_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict__ o
             double *tm = term + 5 * i;
             tm[0] = (double)h.tick; tm[1] = (double)h.nc_obs; tm[2] = (double)h.nc_agent; tm[3] = h.ep_ret; tm[4] = (double)h.ep_len;
         }
-        if (stats) {
-            atomicAdd(&stats[0], 1ull);
-            atomicAdd(&stats[1], (unsigned long long)h.ep_len);
-            atomicAdd(&stats[2], (unsigned long long)__double2ll_rn(h.ep_ret * 1000.0));
-            atomicAdd(&stats[3], (unsigned long long)h.nc_obs);
-            atomicAdd(&stats[4], (h.tick >= (uint32_t)C.timeout_tick) ? 1ull : 0ull);
-            atomicAdd(&stats[5], (unsigned long long)h.nc_agent);
-            atomicAdd(&stats[6], (unsigned long long)(h.flags & 1u));
-        }
+        acc[0] = 1; acc[1] = h.ep_len; acc[2] = __double2ll_rn(h.ep_ret * 1000.0); acc[3] = h.nc_obs;
+        acc[4] = (h.tick >= (uint32_t)C.timeout_tick) ? 1 : 0; acc[5] = h.nc_agent; acc[6] = h.flags & 1u;
         if (autoreset) {
             const uint32_t keep = h.flags;
             ma_reset_env(h, sm_car, sm_ob, cbits, A);
@@ -460,6 +448,32 @@ ma_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict__ o
     }
     ma_observe(h, sm_car, sm_ob, A, obs + i * (int64_t)A * D);
     ma_store(h, sm_car, sm_ob, cbits, S, i, n);
+}
+
+template <bool CONT, bool EXACT>
+__global__ void __launch_bounds__(kMaBlock)
+ma_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew,
+               uint8_t *__restrict__ done_out, double *__restrict__ term, unsigned long long *__restrict__ stats,
+               const MaConsts C, const uint64_t seed, const uint64_t env_id0, const int64_t n, const int flags)
+{
+    extern __shared__ double sm_dyn[];
+    double *sm_car = sm_dyn;                                   // [A][C_NF][kMaBlock]
+    double *sm_ob = sm_dyn + (size_t)S.A * C_NF * kMaBlock;    // [K][O_NF][kMaBlock]
+    const int64_t i = (int64_t)blockIdx.x * kMaBlock + threadIdx.x;
+    long long acc[7] = {0, 0, 0, 0, 0, 0, 0};  // this thread's finished episode, summed per warp at the end
+    if (i < n) ma_step_env<CONT, EXACT>(S, sm_car, sm_ob, actions, obs, rew, done_out, term, C, seed, env_id0, n, flags, i, acc);
+    if (stats) {
+        const long long eps = warp_sum(acc[0]);
+        if (eps != 0) {
+#pragma unroll
+            for (int j = 1; j < 7; ++j) acc[j] = warp_sum(acc[j]);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&stats[0], (unsigned long long)eps);
+#pragma unroll
+                for (int j = 1; j < 7; ++j) atomicAdd(&stats[j], (unsigned long long)acc[j]);
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kMaBlock)

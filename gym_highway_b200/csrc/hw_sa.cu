@@ -323,6 +323,7 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
     const bool inf_obs = !(flags & HW_FLAG_NO_INF_OBS);
     const bool autoreset = !(flags & HW_FLAG_NO_AUTORESET);
     const double dt = K.dt;
+    long long acc_eps = 0, acc_len = 0, acc_ret = 0, acc_col = 0, acc_to = 0;  // finished episodes of this thread
 
     if (i < n) {
         SaEnv e;
@@ -390,13 +391,7 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                 const int er = (was_reset ? 0 : (int)st.z) + ret_milli_step;
                 const uint32_t el = (was_reset ? 0u : st.w) + len_step;
                 if (term) term[i] = make_int4((int)tick, (int)nc, er, (int)el);
-                if (stats) {
-                    atomicAdd(&stats[0], 1ull);
-                    atomicAdd(&stats[1], (unsigned long long)el);
-                    atomicAdd(&stats[2], (unsigned long long)(long long)er);
-                    atomicAdd(&stats[3], (unsigned long long)nc);
-                    if (ncol == 0) atomicAdd(&stats[4], 1ull);
-                }
+                acc_eps += 1; acc_len += el; acc_ret += er; acc_col += nc; acc_to += (ncol == 0) ? 1 : 0;
                 if (autoreset) {
                     sa_reset_env(e);
 #pragma unroll
@@ -417,6 +412,19 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
         }
     }
     store_obs_warp(sm_tile, obs, warp_base, n);
+    if (stats) {  // all 32 lanes are here (warps entirely out of range returned at the top)
+        const long long eps = warp_sum(acc_eps);
+        if (eps != 0) {
+            const long long len = warp_sum(acc_len), ret = warp_sum(acc_ret), col = warp_sum(acc_col), to = warp_sum(acc_to);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&stats[0], (unsigned long long)eps);
+                atomicAdd(&stats[1], (unsigned long long)len);
+                atomicAdd(&stats[2], (unsigned long long)ret);
+                atomicAdd(&stats[3], (unsigned long long)col);
+                atomicAdd(&stats[4], (unsigned long long)to);
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kSaBlock)
