@@ -40,8 +40,8 @@ def _policy(rng, kind, continuous, t, prev):
     return int(rng.choice([2, 3, 3, 0, 1]))  # maintain-heavy
 
 
-def gen_sa(continuous, nsteps, seed, real_time=False):
-    ref = rh.RefSingleAgent(continuous=continuous, real_time=real_time)
+def gen_sa(continuous, nsteps, seed, real_time=False, inf_obs=True):
+    ref = rh.RefSingleAgent(continuous=continuous, real_time=real_time, inf_obs=inf_obs)
     rng = np.random.RandomState(seed)
     rec = {k: [] for k in ("in_car", "in_lane", "in_flags", "in_tick", "in_obst", "in_ncoll", "in_spawn_ctr",
                            "env_id", "action", "out_car", "out_lft", "out_obst", "out_obs", "out_rew", "out_done",
@@ -82,6 +82,7 @@ def gen_sa(continuous, nsteps, seed, real_time=False):
     out["seed"] = np.int64(seed)
     out["continuous"] = np.bool_(continuous)
     out["real_time"] = np.bool_(real_time)
+    out["inf_obs"] = np.bool_(inf_obs)
     return out
 
 
@@ -94,7 +95,8 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     jobs = [("sa_discrete", lambda: gen_sa(False, args.sa_steps, 11)),
             ("sa_continuous", lambda: gen_sa(True, args.sa_steps, 12)),
-            ("sa_discrete_realtime", lambda: gen_sa(False, max(args.sa_steps // 3, 300), 13, real_time=True))]
+            ("sa_discrete_realtime", lambda: gen_sa(False, max(args.sa_steps // 3, 300), 13, real_time=True)),
+            ("sa_discrete_noinf", lambda: gen_sa(False, max(args.sa_steps // 3, 300), 14, inf_obs=False))]
     try:
         from .gen_golden_ma import ma_jobs
         jobs += ma_jobs(args.ma_steps)

@@ -32,8 +32,8 @@ def _actions(rng, kind, continuous, A, prev):
     return rng.choice([2, 3, 3, 3], A)  # accelerate / maintain only: no lane changes, time-outs happen
 
 
-def gen_ma(A, continuous, nsteps, seed, shared_reward=False):
-    ref = rh.RefMultiAgent(A, continuous=continuous, shared_reward=shared_reward)
+def gen_ma(A, continuous, nsteps, seed, shared_reward=False, real_time=False, inf_obs=True):
+    ref = rh.RefMultiAgent(A, continuous=continuous, shared_reward=shared_reward, real_time=real_time, inf_obs=inf_obs)
     rng = np.random.RandomState(seed)
     names = ("in_car", "in_lane", "in_cflags", "in_tick", "in_leader", "in_nobs", "in_obst", "in_olane", "in_ofresh",
              "in_newest", "in_nc_obs", "in_nc_agent", "in_spawn_ctr", "env_id", "action",
@@ -73,7 +73,7 @@ def gen_ma(A, continuous, nsteps, seed, shared_reward=False):
             st.spawn_ctr[0] = prov.spawn_ctr
             st.quantise_f32()
     out = {k: np.asarray(v) for k, v in rec.items()}
-    out.update(seed=np.int64(seed), continuous=np.bool_(continuous), real_time=np.bool_(False), num_agents=np.int64(A),
+    out.update(seed=np.int64(seed), continuous=np.bool_(continuous), real_time=np.bool_(real_time), inf_obs=np.bool_(inf_obs), num_agents=np.int64(A),
                num_slots=np.int64(K), shared_reward=np.bool_(shared_reward))
     return out
 
@@ -84,4 +84,6 @@ def ma_jobs(nsteps):
         jobs.append(("ma%d_discrete" % A, (lambda A=A: gen_ma(A, False, nsteps, 100 + A))))
         jobs.append(("ma%d_continuous" % A, (lambda A=A: gen_ma(A, True, nsteps, 200 + A))))
     jobs.append(("ma5_discrete_shared", lambda: gen_ma(5, False, max(nsteps // 3, 200), 301, shared_reward=True)))
+    jobs.append(("ma3_discrete_realtime", lambda: gen_ma(3, False, max(nsteps // 3, 200), 302, real_time=True)))
+    jobs.append(("ma3_continuous_noinf", lambda: gen_ma(3, True, max(nsteps // 3, 200), 303, inf_obs=False)))
     return jobs

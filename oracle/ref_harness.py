@@ -99,9 +99,9 @@ def _set_rect(sprite):
 class RefSingleAgent(object):
     """one reference HighwayEnv / HighwayEnvContinuous with state injection"""
 
-    def __init__(self, continuous=False, real_time=False):
+    def __init__(self, continuous=False, real_time=False, inf_obs=True):
         m = load()
-        kw = dict(TRAIN_KW, real_time=real_time)
+        kw = dict(TRAIN_KW, real_time=real_time, inf_obs=inf_obs)
         self.env = (m['sa'].HighwayEnvContinuous if continuous else m['sa'].HighwayEnv)(**kw)
         self.continuous = continuous
         self.sim = self.env.env
@@ -173,9 +173,9 @@ class RefSingleAgent(object):
 class RefMultiAgent(object):
     """one reference MultiAgentEnv / MultiAgentEnvContinuous with state injection (A <= 5 cars)"""
 
-    def __init__(self, num_agents, continuous=False, real_time=False, shared_reward=False):
+    def __init__(self, num_agents, continuous=False, real_time=False, shared_reward=False, inf_obs=True):
         m = load()
-        kw = dict(TRAIN_KW, real_time=real_time)
+        kw = dict(TRAIN_KW, real_time=real_time, inf_obs=inf_obs)
         cls = m['ma'].MultiAgentEnvContinuous if continuous else m['ma'].MultiAgentEnv
         self.env = cls(world_config=kw, num_agents=num_agents, shared_reward=shared_reward)
         self.world = self.env.world

@@ -9,7 +9,7 @@ from helpers import MA_STATE_FIELDS, bits_equal, f32, load_golden, ma_state_from
 pytestmark = pytest.mark.gpu
 
 MA_GOLDEN = ["ma1_discrete", "ma1_continuous", "ma3_discrete", "ma3_continuous", "ma5_discrete", "ma5_continuous",
-             "ma5_discrete_shared"]
+             "ma5_discrete_shared", "ma3_discrete_realtime", "ma3_continuous_noinf"]
 
 
 def _env(n, A, **kw):
@@ -48,7 +48,8 @@ def test_golden_transitions(name):
     A, K = int(g["num_agents"]), int(g["num_slots"])
     n = len(g["env_id"])
     env = _env(n, A, continuous=bool(g["continuous"]), seed=int(g["seed"]), env_id0=0, auto_reset=False,
-               shared_reward=bool(g["shared_reward"]), num_slots=K, exact_steering=True)
+               shared_reward=bool(g["shared_reward"]), num_slots=K, exact_steering=True,
+               world_config=dict(real_time=bool(g["real_time"]), inf_obs=bool(g.get("inf_obs", True))))
     _load_state(env, ma_state_from_golden(g))
     obs, rew, done, _ = env.step(torch.from_numpy(np.ascontiguousarray(g["action"])).cuda())
     got = _read_state(env)

@@ -54,14 +54,15 @@ def test_reset_observation_matches_oracle():
     assert np.array_equal(got.lane, st.lane) and np.array_equal(got.tick, st.tick)
 
 
-@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime"])
+@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime", "sa_discrete_noinf"])
 def test_golden_transitions(name):
     """reference-recorded transitions: one env per transition, env_id taken from the file"""
     g = load_golden(name)
     cont, rt, seed = bool(g["continuous"]), bool(g["real_time"]), int(g["seed"])
     n = len(g["out_done"])
     assert np.array_equal(g["env_id"], np.arange(n))  # transition i was recorded as environment i
-    env = _env(n, continuous=cont, real_time=rt, seed=seed, env_id0=0, auto_reset=False, exact_steering=True)
+    env = _env(n, continuous=cont, real_time=rt, seed=seed, env_id0=0, auto_reset=False, exact_steering=True,
+               inf_obs=bool(g.get("inf_obs", True)))
     _load_state(env, sa_state_from_golden(g))
     obs, rew, done, _ = env.step(torch.from_numpy(np.ascontiguousarray(g["action"])).cuda())
     got = _read_state(env)
@@ -210,12 +211,12 @@ def _float_report(name, got, want, max_bitdiff_frac):
     return frac
 
 
-@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime"])
+@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime", "sa_discrete_noinf"])
 def test_fast_mode_golden_transitions(name):
     g = load_golden(name)
     n = len(g["out_done"])
     env = _env(n, continuous=bool(g["continuous"]), real_time=bool(g["real_time"]), seed=int(g["seed"]), env_id0=0,
-               auto_reset=False)
+               auto_reset=False, inf_obs=bool(g.get("inf_obs", True)))
     _load_state(env, sa_state_from_golden(g))
     obs, rew, done, _ = env.step(torch.from_numpy(np.ascontiguousarray(g["action"])).cuda())
     got = _read_state(env)
