@@ -14,67 +14,12 @@
 // reproduces by construction.  The fp32 state is promoted to fp64 in SHARED memory for the duration of the
 // step ([field][thread] layout: every access is conflict free), the ticks run op-for-op like the reference,
 // and the state is rounded back to fp32 once at the end.
-#include "hw_common.cuh"
-#include "../../include/highway_b200.h"
+#include "hw_ma_common.cuh"
 
 namespace hw {
 
-constexpr int kMaBlock = 64;
-constexpr int kMaxA = HW_MA_MAX_AGENTS;
-constexpr int kMaxK = HW_MA_MAX_SLOTS;
-
-// car fields in shared memory
-enum { C_PX = 0, C_PY, C_RX, C_VX, C_VY, C_ACC, C_STEER, C_CRUISE, C_NF };
-enum { O_PX = 0, O_RX, O_VX, O_IV, O_NF };
-
-struct MaPtrs {
-    float *cars;
-    float4 *obst;
-    uint32_t *head;
-    int A, K;
-};
-
-struct MaConsts {
-    double dt, k30dt;
-    int ticks_per_step, timeout_tick;
-};
-
-struct MaHead {
-    uint32_t tick, leader, nobs;
-    uint32_t newest[3];  // slot index, 31 = retired
-    uint32_t olane;      // 2 bits per slot
-    uint32_t ofresh;     // bit k: slot k still carries pygame's default rect (0,0,76,38)
-    uint32_t flags;      // bit 0: a spawn was dropped for lack of slots, bit 1: a lane had no obstacle to observe
-    uint32_t nc_obs, nc_agent, spawn_ctr, ep_len;
-    double ep_ret;
-};
-
 #define CAR(a, f) sm_car[((a) * C_NF + (f)) * kMaBlock + threadIdx.x]
 #define OB(k, f) sm_ob[((k) * O_NF + (f)) * kMaBlock + threadIdx.x]
-
-__device__ __forceinline__ void ma_load_head(MaHead &h, const MaPtrs &S, int64_t i, int64_t n)
-{
-    const uint32_t w0 = S.head[i], w1 = S.head[n + i];
-    h.tick = w0 & 0xFFFFu; h.leader = (w0 >> 16) & 7u; h.nobs = (w0 >> 20) & 31u;
-    h.newest[0] = w1 & 31u; h.newest[1] = (w1 >> 5) & 31u; h.newest[2] = (w1 >> 10) & 31u;
-    h.olane = S.head[2 * n + i];
-    const uint32_t w3 = S.head[3 * n + i];
-    h.ofresh = w3 & 0xFFFFu; h.flags = w3 >> 16;
-    h.nc_obs = S.head[4 * n + i]; h.nc_agent = S.head[5 * n + i]; h.spawn_ctr = S.head[6 * n + i]; h.ep_len = S.head[7 * n + i];
-    h.ep_ret = __hiloint2double((int)S.head[9 * n + i], (int)S.head[8 * n + i]);
-}
-
-__device__ __forceinline__ void ma_store_head(const MaHead &h, const MaPtrs &S, int64_t i, int64_t n)
-{
-    S.head[i] = h.tick | (h.leader << 16) | (h.nobs << 20);
-    S.head[n + i] = h.newest[0] | (h.newest[1] << 5) | (h.newest[2] << 10);
-    S.head[2 * n + i] = h.olane;
-    S.head[3 * n + i] = h.ofresh | (h.flags << 16);
-    S.head[4 * n + i] = h.nc_obs; S.head[5 * n + i] = h.nc_agent; S.head[6 * n + i] = h.spawn_ctr; S.head[7 * n + i] = h.ep_len;
-    S.head[8 * n + i] = (uint32_t)__double2loint(h.ep_ret); S.head[9 * n + i] = (uint32_t)__double2hiint(h.ep_ret);
-}
-
-__device__ __forceinline__ int ob_lane(const MaHead &h, int k) { return (int)((h.olane >> (2 * k)) & 3u); }
 
 // start grid: simple_base.py:32-43 ("X" formation, three obstacles behind the cars); counters of the episode cleared
 __device__ __forceinline__ void ma_reset_env(MaHead &h, double *sm_car, double *sm_ob, uint32_t *cbits, int A)
@@ -289,20 +234,6 @@ __device__ __forceinline__ void ma_tick(MaHead &h, double *sm_car, double *sm_ob
         if (no + na > 0) { done |= 1u << a; rewards[a] = -250.0; }
         else rewards[a] = dsub(ddiv(CAR(a, C_VX), 20.0), 1.0);
     }
-}
-
-// (v - lo) / (hi - lo) in float64, cast to float32 (MultiAgentEnv._get_obs_norm normalises in float64; the
-// VecEnv buffer is float32).  The division is q = fma(fma(-q0, c, x), rc, q0), q0 = x*rc, rc = RN(1/c):
-// Markstein's correction, which returns the correctly rounded quotient (checked against IEEE division on 10^9
-// random operands per constant, scripts/verify_div_by_const.c).
-__device__ __forceinline__ float norm_f64(double raw, const double lo, const double hi)
-{
-    double v = (double)(float)raw;  // np.array(..., dtype=float32)
-    v = (v < lo) ? lo : v;
-    v = (v > hi) ? hi : v;
-    const double x = dsub(v, lo), c = hi - lo, rc = 1.0 / c;
-    const double q0 = dmul(x, rc);
-    return (float)__fma_rn(__fma_rn(-q0, c, x), rc, q0);
 }
 
 // Scenario.observations for every car, written straight to global memory (row = env, car)
