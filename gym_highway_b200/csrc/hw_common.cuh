@@ -22,10 +22,28 @@ __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a,
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
 // python max(lo, min(x, hi)): min keeps x unless hi < x, max keeps lo unless inner > lo
+// The max is spelled in PTX: NVVM turns the C++ ternary into max.f64, whose NaN-aware expansion on sm_100a is
+// six instructions (DSETP.MAX, two moves, SEL, FSEL, a predicated LOP3) instead of a compare and two selects.
+__device__ __forceinline__ double py_max(double lo, double x)  // x if x > lo else lo
+{
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(x), "d"(lo));
+    return r;
+}
+
+// p ? a : b as selp.f64 (two 32-bit selects); spelled in PTX where NVVM would otherwise turn a chain of
+// selects into divergent branches
+__device__ __forceinline__ double dsel(bool p, double a, double b)
+{
+    double r;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\tselp.f64 %0, %1, %2, q;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
+    return r;
+}
+
 __device__ __forceinline__ double py_clamp(double x, double lo, double hi)
 {
     const double inner = (hi < x) ? hi : x;
-    return (inner > lo) ? inner : lo;
+    return py_max(lo, inner);
 }
 
 __device__ __forceinline__ double lane_centre(int k)  // k = lane-1: 1.25, 3.75, 6.25

@@ -107,6 +107,34 @@ struct SaConsts {
     int timeout_tick;
 };
 
+// respawn (multi_lane_sim.py:963-991): opx < -2.375, pre-filtered on the hi words (negative doubles order reversed)
+__device__ __forceinline__ void sa_respawn(SaEnv &e, const double dt, const bool l1, const bool l2,
+                                           const uint64_t seed, const uint64_t env_id)
+{
+    constexpr uint32_t kNeg = 0xC0030000u;  // hi(-2.375); hi >= kNeg  <=>  opx <= -2.375 (- a few ulps of slack)
+    if (max(max(hi32(e.opx[0]), hi32(e.opx[1])), hi32(e.opx[2])) >= kNeg) {
+        // lanes in ascending order; x = U(70,100) then v = U(5,7) from one Philox block per spawn
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+            const double o = (k == 0) ? e.opx[0] : (k == 1) ? e.opx[1] : e.opx[2];
+            if (o < -2.375) {
+                double u1, u2;
+                spawn_uniforms(seed, env_id, e.spawn_ctr, u1, u2);
+                e.spawn_ctr += 1;
+                const double x = dadd(70.0, dmul(30.0, u1));
+                const double v = dadd(5.0, dmul(2.0, u2));
+                const double r = dadd(e.rx, dsub(x, 10.0));  // leader.raw_x + (x - leader.x), the leader sits at x = 10
+                const double d = dmul(v, dt);
+                if (k == 0) { e.opx[0] = x; e.orx[0] = r; e.oiv[0] = v; e.odt[0] = d; }
+                else if (k == 1) { e.opx[1] = x; e.orx[1] = r; e.oiv[1] = v; e.odt[1] = d; }
+                else { e.opx[2] = x; e.orx[2] = r; e.oiv[2] = v; e.odt[2] = d; }
+            }
+        }
+        // a fresh obstacle is far ahead (x >= 70): it cannot be the held-back one
+        e.slow = e.slow && sel_lane(l1, l2, e.opx[0], e.opx[1], e.opx[2]) < 10.0;
+    }
+}
+
 // One simulator tick (multi_lane_sim.py:879-1049).  Returns the number of obstacle rects the car
 // overlapped (0 when the collision lock is on); the tick reward is -250*n, or vx/20-1 when n == 0.
 //
@@ -228,31 +256,121 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
         }
     }
 
-    // ---- respawn (:963-991): opx < -2.375, pre-filtered on the hi words (negative doubles order reversed) ----
-    if (inf_obs) {
-        constexpr uint32_t kNeg = 0xC0030000u;  // hi(-2.375); hi >= kNeg  <=>  opx <= -2.375 (- a few ulps of slack)
-        if (max(max(hi32(e.opx[0]), hi32(e.opx[1])), hi32(e.opx[2])) >= kNeg) {
-            // lanes in ascending order; x = U(70,100) then v = U(5,7) from one Philox block per spawn
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k) {
-                const double o = (k == 0) ? e.opx[0] : (k == 1) ? e.opx[1] : e.opx[2];
-                if (o < -2.375) {
-                    double u1, u2;
-                    spawn_uniforms(seed, env_id, e.spawn_ctr, u1, u2);
-                    e.spawn_ctr += 1;
-                    const double x = dadd(70.0, dmul(30.0, u1));
-                    const double v = dadd(5.0, dmul(2.0, u2));
-                    const double r = dadd(e.rx, dsub(x, 10.0));  // leader.raw_x + (x - leader.x), the leader sits at x = 10
-                    const double d = dmul(v, dt);
-                    if (k == 0) { e.opx[0] = x; e.orx[0] = r; e.oiv[0] = v; e.odt[0] = d; }
-                    else if (k == 1) { e.opx[1] = x; e.orx[1] = r; e.oiv[1] = v; e.odt[1] = d; }
-                    else { e.opx[2] = x; e.orx[2] = r; e.oiv[2] = v; e.odt[2] = d; }
-                }
-            }
-            // a fresh obstacle is far ahead (x >= 70): it cannot be the held-back one
-            e.slow = e.slow && sel_lane(l1, l2, e.opx[0], e.opx[1], e.opx[2]) < 10.0;
+    // ---- respawn (:963-991) ----
+    if (inf_obs) sa_respawn(e, dt, l1, l2, seed, env_id);
+    return ncol;
+}
+
+// Ticks 2..T of a DISCRETE step.  Same arithmetic as sa_tick<false, false, .>, restated around what the first tick
+// of the step has already established, to shrink the instruction stream the kernel is bound by:
+//   * the car is pinned at px = 10; acc is in [-5, 5 + dt] and only the accelerate() branch can see a value
+//     above 5, so the action stage's clamp of acc folds into that branch; steer is non-zero only while a
+//     lane-change mode is set, and py only moves (and only then needs the road clamp) on a steering tick;
+//   * the action of the step has fired on its first tick, so it can only fire again after the simulator
+//     cleared the mode it asks for (lane reached, maintain snapped): that whole stage sits behind a branch;
+//   * signs and "< 10.0" are read from the hi words (integer pipe) instead of fp64 compares.
+template <bool EXACT>
+__device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncoll_acc, const SaConsts &K, const bool inf_obs,
+                                             const uint32_t amask, const uint32_t apair, const int dlane,
+                                             const uint64_t seed, const uint64_t env_id)
+{
+    const double dt = K.dt;
+    uint32_t b = e.bits + 1;
+
+    // ---- apply action (multi_lane_sim.py:502-517, :529-572) ----
+    // Not rare: an env whose action is MAINTAIN with nobody ahead snaps and re-fires on every tick, and so does a
+    // LEFT/RIGHT against the edge of the road, so the stage stays branch-free.  The two modes of a pair exclude
+    // each other, hence setting the requested bit and clearing its partner is the identity when nothing fires.
+    const uint32_t fire = amask & ~b;
+    b = (b & ~apair) | amask;
+    // lane id in its own register for the duration of the loop (the field in `bits` is refreshed after it);
+    // dlane = -1 / +1 / 0 for LEFT / RIGHT / the other actions is fixed for the step
+    lane = (fire & (kBitLeft | kBitRight)) ? min(max(lane + dlane, 1), 3) : lane;
+    const bool l1 = lane == 1, l2 = lane == 2, l3 = lane == 3;
+    const double fpx = sel_lane(l1, l2, e.opx[0], e.opx[1], e.opx[2]);
+    const double fiv = sel_lane(l1, l2, e.oiv[0], e.oiv[1], e.oiv[2]);
+    {
+        const double fvx = e.slow ? e.vx : fiv;
+        const double cr = (fpx > 10.0) ? fvx : e.vx;
+        e.cruise = (fire & kBitDoMaint) ? cr : e.cruise;
+    }
+
+    // ---- collision test on the rects the previous tick left (:920-937) ----
+    // The car's rect x is 282, so obstacle k overlaps in x iff 207 <= trunc(opx*32-38) <= 357 iff 7.65625 <= opx < 12.375
+    // (the scaling and the subtraction are exact there); the hi-word window below is a superset, and roughly every
+    // second tick some lane of a warp passes it (obstacles in the other lanes drift past the car all the time), so
+    // the exact test behind it is kept short: the y overlap of rect k (y = 21 + 80k, height 38) with the car's rect
+    // is |ay - by| <= 37.
+    int ncol = 0;
+    {
+        constexpr uint32_t kLo = 0x401EA000u, kSpan = 0x4028C000u - 0x401EA000u;  // hi(7.65625), hi(12.375)
+        const bool n0 = hi32(e.opx[0]) - kLo <= kSpan, n1 = hi32(e.opx[1]) - kLo <= kSpan, n2 = hi32(e.opx[2]) - kLo <= kSpan;
+        if (n0 | n1 | n2) {
+            const int ay = rect_y(e.py);
+            const bool c0 = n0 && e.opx[0] >= 7.65625 && e.opx[0] < 12.375 && (uint32_t)(ay - 21 + 37) <= 74u;
+            const bool c1 = n1 && e.opx[1] >= 7.65625 && e.opx[1] < 12.375 && (uint32_t)(ay - 101 + 37) <= 74u;
+            const bool c2 = n2 && e.opx[2] >= 7.65625 && e.opx[2] < 12.375 && (uint32_t)(ay - 181 + 37) <= 74u;
+            ncol = (c0 ? 1 : 0) + (c1 ? 1 : 0) + (c2 ? 1 : 0);
+            ncoll_acc += ncol;
         }
     }
+
+    // ---- car update (:185-229) ----
+    const bool m_acc = (b & kBitDoAcc) != 0;
+    const bool m_maint = (b & kBitDoMaint) != 0;  // never set together with do_accelerate
+    {
+        // accelerate(): acc = 0 if acc < 0 else acc + dt, on the acc the action stage clamped to <= 5
+        const double acc_c = (5.0 < e.acc) ? 5.0 : e.acc;
+        const double acc_p = dadd(acc_c, dt);
+        const bool neg = __double2hiint(e.acc) < 0;  // acc is never -0.0
+        // maintain(): bang-bang towards ceil(cruise), snap when the ceilings agree
+        const double vc = ceil(e.vx), cc = ceil(e.cruise);
+        const bool snap = m_maint & (vc == cc);
+        const double acc_m = __hiloint2double(snap ? 0 : ((vc <= cc) ? 0x40140000 : (int)0xC0140000), 0);  // 0.0, 5.0, -5.0
+        const double acc_a = dsel(neg, 0.0, acc_p);
+        e.acc = dsel(m_acc, acc_a, dsel(m_maint, acc_m, e.acc));
+        e.vx = snap ? e.cruise : e.vx;
+        if (m_acc & (e.acc == 5.0)) b &= ~kBitDoAcc;
+        if (snap) b &= ~kBitDoMaint;
+    }
+    {
+        const double v = dadd(e.vx, dmul(e.acc, dt));
+        const double top = (20.0 < v) ? 20.0 : v;
+        // max(0.0, top): top unless top <= 0, i.e. unless its sign bit is set or it is +0.0 (where both agree)
+        e.vx = (__double2hiint(top) < 0) ? 0.0 : top;
+    }
+    const double vdt = dmul(e.vx, dt);
+    e.rx = dadd(e.rx, vdt);
+    const bool m_left = (b & kBitLeft) != 0;
+    const bool m_right = (b & kBitRight) != 0;  // never set together with left_mode
+    if (m_left | m_right) {
+        // steering clamp of the action stage (only a lane-change mode leaves steer != 0), then moveLeft/moveRight
+        const double sa = fabs(e.steer);
+        const double sc = (30.0 < sa) ? copysign(30.0, e.steer) : e.steer;
+        double st = dadd(sc, m_left ? K.k30dt : -K.k30dt);
+        const double ty = __hiloint2double(l1 ? 0x3FF40000 : (l2 ? 0x400E0000 : 0x40190000), 0);  // 1.25, 3.75, 6.25
+        const bool reached = (m_left && e.py <= ty) || (m_right && e.py >= ty);
+        if (reached) { st = 0.0; b &= ~(kBitLeft | kBitRight); }
+        e.steer = st;
+        if (st != 0.0) {
+            const double ang = angular_velocity<EXACT>(e.vx, st);
+            e.py = road_clamp<false>(dsub(e.py, dmul(dmul(dmul(ang, kRad2Deg), dt), dt)));
+        }
+    }
+    e.bits = b;
+
+    // ---- obstacle update (:324-347): only the obstacle in the car's lane can be held back ----
+    {
+        e.slow = (__double2hiint(fpx) < 0x40240000) & (e.vx < fiv);  // fpx < 10.0 read off the hi word
+        const bool s0 = l1 & e.slow, s1 = l2 & e.slow, s2 = l3 & e.slow;
+        const double d0 = s0 ? vdt : e.odt[0], d1 = s1 ? vdt : e.odt[1], d2 = s2 ? vdt : e.odt[2];
+        e.opx[0] = dsub(dadd(e.opx[0], d0), vdt); e.orx[0] = dadd(e.orx[0], d0);
+        e.opx[1] = dsub(dadd(e.opx[1], d1), vdt); e.orx[1] = dadd(e.orx[1], d1);
+        e.opx[2] = dsub(dadd(e.opx[2], d2), vdt); e.orx[2] = dadd(e.orx[2], d2);
+    }
+
+    // ---- respawn (:963-991) ----
+    if (inf_obs) sa_respawn(e, dt, l1, l2, seed, env_id);
     return ncol;
 }
 
@@ -368,13 +486,21 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
             if (!CONT) {  // ACTION_LOOKUP (highway_env.py:14-20) as the mode bit it requests
                 amask = (act_d == HW_ACT_LEFT) ? kBitLeft : (act_d == HW_ACT_RIGHT) ? kBitRight
                       : (act_d == HW_ACT_ACCELERATE) ? kBitDoAcc : (act_d == HW_ACT_MAINTAIN) ? kBitDoMaint : 0u;
-                apair = (amask & (kBitLeft | kBitRight)) ? (kBitLeft | kBitRight) : (kBitDoAcc | kBitDoMaint);
+                apair = (amask & (kBitLeft | kBitRight)) ? (kBitLeft | kBitRight) : amask ? (kBitDoAcc | kBitDoMaint) : 0u;
             }
             // env.step: up to ticks_per_step ticks, stop at the first crash (highway_env.py:99-108)
             int ncol = sa_tick<CONT, true, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
             e.px = 10.0;  // the only car is always the leader (:212-213)
-            for (int t = 1; t < K.ticks_per_step && ncol == 0; ++t)
-                ncol = sa_tick<CONT, false, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
+            if (CONT) {
+                for (int t = 1; t < K.ticks_per_step && ncol == 0; ++t)
+                    ncol = sa_tick<CONT, false, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
+            } else {
+                int lane = (int)((e.bits >> HW_BITS_LANE_SHIFT) & 3u);
+                const int dlane = (act_d == HW_ACT_RIGHT) ? 1 : (act_d == HW_ACT_LEFT) ? -1 : 0;
+                for (int t = 1; t < K.ticks_per_step && ncol == 0; ++t)
+                    ncol = sa_tick_later<EXACT>(e, lane, ncoll_step, K, inf_obs, amask, apair, dlane, seed, env_id);
+                e.bits = (e.bits & ~(3u << HW_BITS_LANE_SHIFT)) | ((uint32_t)lane << HW_BITS_LANE_SHIFT);
+            }
             const uint32_t tick = e.bits & HW_BITS_TICK_MASK;
             const bool timeout = tick >= (uint32_t)K.timeout_tick;
             is_done = timeout || ncol > 0;
