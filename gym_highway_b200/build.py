@@ -40,7 +40,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + srcs
+    extra = os.environ.get("HW_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DHW_SA_MIN_BLOCKS_D=8
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + srcs
     subprocess.check_call(cmd)
     os.replace(LIB + ".tmp", LIB)
     return LIB

@@ -287,12 +287,14 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     // dlane = -1 / +1 / 0 for LEFT / RIGHT / the other actions is fixed for the step
     lane = (fire & (kBitLeft | kBitRight)) ? min(max(lane + dlane, 1), 3) : lane;
     const bool l1 = lane == 1, l2 = lane == 2, l3 = lane == 3;
-    const double fpx = sel_lane(l1, l2, e.opx[0], e.opx[1], e.opx[2]);
-    const double fiv = sel_lane(l1, l2, e.oiv[0], e.oiv[1], e.oiv[2]);
+    double fpx = e.opx[2], fiv = e.oiv[2];
+    dmov_if(l2, fpx, e.opx[1]); dmov_if(l2, fiv, e.oiv[1]);
+    dmov_if(l1, fpx, e.opx[0]); dmov_if(l1, fiv, e.oiv[0]);
     {
-        const double fvx = e.slow ? e.vx : fiv;
-        const double cr = (fpx > 10.0) ? fvx : e.vx;
-        e.cruise = (fire & kBitDoMaint) ? cr : e.cruise;
+        double fvx = fiv, cr = e.vx;
+        dmov_if(e.slow, fvx, e.vx);
+        dmov_if(fpx > 10.0, cr, fvx);
+        dmov_if((fire & kBitDoMaint) != 0, e.cruise, cr);
     }
 
     // ---- collision test on the rects the previous tick left (:920-937) ----
@@ -320,24 +322,25 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     const bool m_maint = (b & kBitDoMaint) != 0;  // never set together with do_accelerate
     {
         // accelerate(): acc = 0 if acc < 0 else acc + dt, on the acc the action stage clamped to <= 5
-        const double acc_c = (5.0 < e.acc) ? 5.0 : e.acc;
-        const double acc_p = dadd(acc_c, dt);
-        const bool neg = __double2hiint(e.acc) < 0;  // acc is never -0.0
+        double acc_c = e.acc;
+        dmov_if(5.0 < e.acc, acc_c, 5.0);
+        double acc_a = dadd(acc_c, dt);
+        dmov_if(e.acc < 0.0, acc_a, 0.0);
         // maintain(): bang-bang towards ceil(cruise), snap when the ceilings agree
         const double vc = ceil(e.vx), cc = ceil(e.cruise);
         const bool snap = m_maint & (vc == cc);
         const double acc_m = __hiloint2double(snap ? 0 : ((vc <= cc) ? 0x40140000 : (int)0xC0140000), 0);  // 0.0, 5.0, -5.0
-        const double acc_a = dsel(neg, 0.0, acc_p);
-        e.acc = dsel(m_acc, acc_a, dsel(m_maint, acc_m, e.acc));
-        e.vx = snap ? e.cruise : e.vx;
+        dmov_if(m_acc, e.acc, acc_a);
+        dmov_if(m_maint, e.acc, acc_m);
+        dmov_if(snap, e.vx, e.cruise);
         if (m_acc & (e.acc == 5.0)) b &= ~kBitDoAcc;
         if (snap) b &= ~kBitDoMaint;
     }
     {
-        const double v = dadd(e.vx, dmul(e.acc, dt));
-        const double top = (20.0 < v) ? 20.0 : v;
-        // max(0.0, top): top unless top <= 0, i.e. unless its sign bit is set or it is +0.0 (where both agree)
-        e.vx = (__double2hiint(top) < 0) ? 0.0 : top;
+        double v = dadd(e.vx, dmul(e.acc, dt));
+        dmov_if(20.0 < v, v, 20.0);
+        dmov_if(!(v > 0.0), v, 0.0);  // max(0.0, v) is v only when v > 0
+        e.vx = v;
     }
     const double vdt = dmul(e.vx, dt);
     e.rx = dadd(e.rx, vdt);
@@ -345,12 +348,14 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     const bool m_right = (b & kBitRight) != 0;  // never set together with left_mode
     if (m_left | m_right) {
         // steering clamp of the action stage (only a lane-change mode leaves steer != 0), then moveLeft/moveRight
-        const double sa = fabs(e.steer);
-        const double sc = (30.0 < sa) ? copysign(30.0, e.steer) : e.steer;
-        double st = dadd(sc, m_left ? K.k30dt : -K.k30dt);
+        double sc = e.steer, inc = K.k30dt;
+        dmov_if(30.0 < fabs(e.steer), sc, copysign(30.0, e.steer));
+        dmov_if(m_right, inc, -K.k30dt);
+        double st = dadd(sc, inc);
         const double ty = __hiloint2double(l1 ? 0x3FF40000 : (l2 ? 0x400E0000 : 0x40190000), 0);  // 1.25, 3.75, 6.25
         const bool reached = (m_left && e.py <= ty) || (m_right && e.py >= ty);
-        if (reached) { st = 0.0; b &= ~(kBitLeft | kBitRight); }
+        dmov_if(reached, st, 0.0);
+        if (reached) b &= ~(kBitLeft | kBitRight);
         e.steer = st;
         if (st != 0.0) {
             const double ang = angular_velocity<EXACT>(e.vx, st);
@@ -361,9 +366,9 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
 
     // ---- obstacle update (:324-347): only the obstacle in the car's lane can be held back ----
     {
-        e.slow = (__double2hiint(fpx) < 0x40240000) & (e.vx < fiv);  // fpx < 10.0 read off the hi word
-        const bool s0 = l1 & e.slow, s1 = l2 & e.slow, s2 = l3 & e.slow;
-        const double d0 = s0 ? vdt : e.odt[0], d1 = s1 ? vdt : e.odt[1], d2 = s2 ? vdt : e.odt[2];
+        e.slow = (fpx < 10.0) & (e.vx < fiv);
+        double d0 = dmul(e.oiv[0], dt), d1 = dmul(e.oiv[1], dt), d2 = dmul(e.oiv[2], dt);
+        dmov_if(l1 & e.slow, d0, vdt); dmov_if(l2 & e.slow, d1, vdt); dmov_if(l3 & e.slow, d2, vdt);
         e.opx[0] = dsub(dadd(e.opx[0], d0), vdt); e.orx[0] = dadd(e.orx[0], d0);
         e.opx[1] = dsub(dadd(e.opx[1], d1), vdt); e.orx[1] = dadd(e.orx[1], d1);
         e.opx[2] = dsub(dadd(e.opx[2], d2), vdt); e.orx[2] = dadd(e.orx[2], d2);
@@ -420,7 +425,7 @@ __device__ __forceinline__ void store_obs_warp(float *sm_tile, float *__restrict
 // Resident blocks per SM the register allocator is asked to make room for (measured on B200 at 4M envs:
 // discrete 5 -> 7.9e9, 6 -> 8.5e9, 8 -> 8.5e9 env-steps/s; continuous 6 -> 8.8e9, 8 -> 9.2e9).
 #ifndef HW_SA_MIN_BLOCKS_D
-#define HW_SA_MIN_BLOCKS_D 6
+#define HW_SA_MIN_BLOCKS_D 8
 #endif
 #ifndef HW_SA_MIN_BLOCKS_C
 #define HW_SA_MIN_BLOCKS_C 8
@@ -431,8 +436,10 @@ __global__ void __launch_bounds__(kSaBlock, CONT ? HW_SA_MIN_BLOCKS_C : HW_SA_MI
 sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew,
                uint8_t *__restrict__ done, int4 *__restrict__ term, unsigned long long *__restrict__ stats,
                const SaConsts K, const uint64_t seed, const uint64_t env_id0, const uint64_t action_ctr0,
-               const int steps, const int64_t n, const int flags)
+               const int steps_arg, const int64_t n, const int flags)
 {
+    const int steps = RANDOM_ACTIONS ? steps_arg : 1;  // step() proper is one step per launch: lets the episode bookkeeping fold
+
     __shared__ __align__(16) float sm_obs[kSaBlock * HW_SA_OBS_DIM];
     const int64_t i = (int64_t)blockIdx.x * kSaBlock + threadIdx.x;
     const int64_t warp_base = i - (threadIdx.x & 31);

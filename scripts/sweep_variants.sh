@@ -1,0 +1,8 @@
+#!/bin/bash
+# run scripts/perf_sa.py once per prebuilt library variant in build/variants/ (tuning experiments)
+keep=$(mktemp); cp gym_highway_b200/libhighway_b200.so $keep
+for f in build/variants/*.so; do
+  cp $f gym_highway_b200/libhighway_b200.so
+  echo "== $f"; python scripts/perf_sa.py ${1:-4194304} 2>&1 | tail -2
+done
+cp $keep gym_highway_b200/libhighway_b200.so
