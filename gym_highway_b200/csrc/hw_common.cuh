@@ -40,13 +40,20 @@ __device__ __forceinline__ double dsel(bool p, double a, double b)
     return r;
 }
 
-// if (p) x = y, spelled as a branch around a move in PTX.  ptxas turns it into predicated moves (one CS2R when y is
-// zero) instead of the FSEL pair a C++ ternary gives.  The step kernels are bound by the 16-lane ALU pipe that
-// executes FSEL / ISETP / LOP3 (about 70 % busy against 36 % for the fp64 pipe), and a predicated move can be
-// scheduled on the FMA pipe as IMAD.MOV.
+// Conditional moves of doubles, spelled in PTX as a branch around one instruction so that ptxas predicates that
+// instruction instead of emitting the FSEL pair a C++ ternary gives.  Why: the step kernels are bound by
+// instruction issue, and within that by the 16-lane ALU pipe that executes FSEL / ISETP / LOP3 (it was ~70 % busy
+// against 36 % for the fp64 pipe).
+//   dmov_if: if (p) x = y for y in a register: ONE predicated DMUL by 1.0 (exact for every y, -0.0 included).
+//   dset_if: if (p) x = c for a literal c: predicated moves (a single CS2R / DMUL for zero).
 __device__ __forceinline__ void dmov_if(bool p, double &x, double y)
 {
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmov.f64 %0, %2;\nHW_SKIP:\n\t}" : "+d"(x) : "r"((int)p), "d"(y));
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmul.rn.f64 %0, %2, 0d3FF0000000000000;\nHW_SKIP:\n\t}" : "+d"(x) : "r"((int)p), "d"(y));
+}
+
+__device__ __forceinline__ void dset_if(bool p, double &x, double c)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmov.f64 %0, %2;\nHW_SKIP:\n\t}" : "+d"(x) : "r"((int)p), "d"(c));
 }
 
 __device__ __forceinline__ double py_clamp(double x, double lo, double hi)

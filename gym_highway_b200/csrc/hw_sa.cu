@@ -323,9 +323,9 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     {
         // accelerate(): acc = 0 if acc < 0 else acc + dt, on the acc the action stage clamped to <= 5
         double acc_c = e.acc;
-        dmov_if(5.0 < e.acc, acc_c, 5.0);
+        dset_if(5.0 < e.acc, acc_c, 5.0);
         double acc_a = dadd(acc_c, dt);
-        dmov_if(e.acc < 0.0, acc_a, 0.0);
+        dset_if(e.acc < 0.0, acc_a, 0.0);
         // maintain(): bang-bang towards ceil(cruise), snap when the ceilings agree
         const double vc = ceil(e.vx), cc = ceil(e.cruise);
         const bool snap = m_maint & (vc == cc);
@@ -338,8 +338,8 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     }
     {
         double v = dadd(e.vx, dmul(e.acc, dt));
-        dmov_if(20.0 < v, v, 20.0);
-        dmov_if(!(v > 0.0), v, 0.0);  // max(0.0, v) is v only when v > 0
+        dset_if(20.0 < v, v, 20.0);
+        dset_if(!(v > 0.0), v, 0.0);  // max(0.0, v) is v only when v > 0
         e.vx = v;
     }
     const double vdt = dmul(e.vx, dt);
@@ -354,7 +354,7 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
         double st = dadd(sc, inc);
         const double ty = __hiloint2double(l1 ? 0x3FF40000 : (l2 ? 0x400E0000 : 0x40190000), 0);  // 1.25, 3.75, 6.25
         const bool reached = (m_left && e.py <= ty) || (m_right && e.py >= ty);
-        dmov_if(reached, st, 0.0);
+        dset_if(reached, st, 0.0);
         if (reached) b &= ~(kBitLeft | kBitRight);
         e.steer = st;
         if (st != 0.0) {
