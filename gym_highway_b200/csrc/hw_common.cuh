@@ -21,7 +21,6 @@ __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a,
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
-// python max(lo, min(x, hi)): min keeps x unless hi < x, max keeps lo unless inner > lo
 // The max is spelled in PTX: NVVM turns the C++ ternary into max.f64, whose NaN-aware expansion on sm_100a is
 // six instructions (DSETP.MAX, two moves, SEL, FSEL, a predicated LOP3) instead of a compare and two selects.
 __device__ __forceinline__ double py_max(double lo, double x)  // x if x > lo else lo
@@ -51,15 +50,23 @@ __device__ __forceinline__ void dmov_if(bool p, double &x, double y)
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmul.rn.f64 %0, %2, 0d3FF0000000000000;\nHW_SKIP:\n\t}" : "+d"(x) : "r"((int)p), "d"(y));
 }
 
+// same with the condition given as a word that is non-zero when true (e.g. bits & HW_BIT_x): the test is then one LOP3
+__device__ __forceinline__ void dmov_if_nz(uint32_t w, double &x, double y)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmul.rn.f64 %0, %2, 0d3FF0000000000000;\nHW_SKIP:\n\t}" : "+d"(x) : "r"(w), "d"(y));
+}
+
 __device__ __forceinline__ void dset_if(bool p, double &x, double c)
 {
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmov.f64 %0, %2;\nHW_SKIP:\n\t}" : "+d"(x) : "r"((int)p), "d"(c));
 }
 
-__device__ __forceinline__ double py_clamp(double x, double lo, double hi)
+// python max(lo, min(x, hi)): min keeps x unless hi < x; max keeps lo unless the inner value is > lo
+__device__ __forceinline__ double py_clamp(double x, const double lo, const double hi)
 {
-    const double inner = (hi < x) ? hi : x;
-    return py_max(lo, inner);
+    dset_if(hi < x, x, hi);
+    dset_if(!(x > lo), x, lo);
+    return x;
 }
 
 __device__ __forceinline__ double lane_centre(int k)  // k = lane-1: 1.25, 3.75, 6.25

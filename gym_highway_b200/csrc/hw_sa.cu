@@ -24,7 +24,6 @@ constexpr int kSaBlock = 128;
 struct SaEnv {
     double px, py, rx, vx, acc, steer, cruise;
     double opx[3], orx[3], ovx[3], oiv[3];
-    double odt[3];  // oiv[k] * dt, the per-tick displacement of an obstacle that is not held back
     uint32_t bits;  // tick | lane << 16 | mode flags
     uint32_t spawn_ctr;
     bool slow;      // the obstacle in the car's lane moved with min(init_vx, car vx) == car vx in the last tick
@@ -82,10 +81,10 @@ __device__ __noinline__ int sa_collide_exact(double px, double py, double o0, do
 template <bool CONT>
 __device__ __forceinline__ double road_clamp(double y)
 {
-    // `if y < lo: y = lo  elif y > 6: y = min(y, 7)` == (y < lo) ? lo : min(y, 7): for lo <= y <= 6 the min is the identity
-    const double lo = CONT ? 1.0 : 0.0;
-    const double top = (7.0 < y) ? 7.0 : y;
-    return (y < lo) ? lo : top;
+    // `if y < lo: y = lo  elif y > 6: y = min(y, 7)`: for lo <= y <= 6 the min is the identity
+    dset_if(7.0 < y, y, 7.0);
+    dset_if(y < (CONT ? 1.0 : 0.0), y, CONT ? 1.0 : 0.0);
+    return y;
 }
 
 // hi word of a double; for non-negative values the unsigned order of hi words is the numeric order
@@ -124,10 +123,9 @@ __device__ __forceinline__ void sa_respawn(SaEnv &e, const double dt, const bool
                 const double x = dadd(70.0, dmul(30.0, u1));
                 const double v = dadd(5.0, dmul(2.0, u2));
                 const double r = dadd(e.rx, dsub(x, 10.0));  // leader.raw_x + (x - leader.x), the leader sits at x = 10
-                const double d = dmul(v, dt);
-                if (k == 0) { e.opx[0] = x; e.orx[0] = r; e.oiv[0] = v; e.odt[0] = d; }
-                else if (k == 1) { e.opx[1] = x; e.orx[1] = r; e.oiv[1] = v; e.odt[1] = d; }
-                else { e.opx[2] = x; e.orx[2] = r; e.oiv[2] = v; e.odt[2] = d; }
+                if (k == 0) { e.opx[0] = x; e.orx[0] = r; e.oiv[0] = v; }
+                else if (k == 1) { e.opx[1] = x; e.orx[1] = r; e.oiv[1] = v; }
+                else { e.opx[2] = x; e.orx[2] = r; e.oiv[2] = v; }
             }
         }
         // a fresh obstacle is far ahead (x >= 70): it cannot be the held-back one
@@ -172,16 +170,18 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
     // the obstacle that shares the car's lane (each lane holds exactly one).  A tick never fires both a lane
     // change and MAINTAIN, so the post-action lane is also the lane maintain() looks at.
     bool l1 = lane == 1, l2 = lane == 2;
-    double fpx = sel_lane(l1, l2, e.opx[0], e.opx[1], e.opx[2]);
-    double fiv = sel_lane(l1, l2, e.oiv[0], e.oiv[1], e.oiv[2]);
+    double fpx = e.opx[2], fiv = e.oiv[2];
+    dmov_if(l2, fpx, e.opx[1]); dmov_if(l2, fiv, e.oiv[1]);
+    dmov_if(l1, fpx, e.opx[0]); dmov_if(l1, fiv, e.oiv[0]);
     if (!CONT) {
         // maintain(): cruise = velocity of the nearest vehicle strictly ahead in the lane, else own velocity.  That
         // velocity is what its last update left: the stored one on the first tick, else init_vx or the car's vx.
-        double fvx;
-        if (FIRST) fvx = sel_lane(l1, l2, e.ovx[0], e.ovx[1], e.ovx[2]);
-        else       fvx = e.slow ? e.vx : fiv;
-        const double cr = (fpx > px) ? fvx : e.vx;
-        e.cruise = (fire & kBitDoMaint) ? cr : e.cruise;
+        double fvx = FIRST ? e.ovx[2] : fiv;
+        if (FIRST) { dmov_if(l2, fvx, e.ovx[1]); dmov_if(l1, fvx, e.ovx[0]); }
+        else       dmov_if(e.slow, fvx, e.vx);
+        double cr = e.vx;
+        dmov_if(fpx > px, cr, fvx);
+        dmov_if_nz(fire & kBitDoMaint, e.cruise, cr);
     }
 
     // ---- collision test on the rects the previous tick left (:920-937) ----
@@ -204,13 +204,15 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
         const bool m_acc = (b & kBitDoAcc) != 0;
         const bool m_maint = (b & kBitDoMaint) != 0;  // never set together with do_accelerate
         // accelerate(): acc = 0 if acc < 0 else acc + dt ; `acc == 5.0` clears the mode
-        const double acc_a = (e.acc < 0.0) ? 0.0 : dadd(e.acc, dt);
+        double acc_a = dadd(e.acc, dt);
+        dset_if(e.acc < 0.0, acc_a, 0.0);
         // maintain(): bang-bang towards ceil(cruise), snap when the ceilings agree
         const double vc = ceil(e.vx), cc = ceil(e.cruise);
         const bool snap = m_maint && vc == cc;
-        const double acc_m = snap ? 0.0 : ((vc <= cc) ? 5.0 : -5.0);
-        e.acc = m_acc ? acc_a : (m_maint ? acc_m : e.acc);
-        e.vx = snap ? e.cruise : e.vx;
+        const double acc_m = __hiloint2double(snap ? 0 : ((vc <= cc) ? 0x40140000 : (int)0xC0140000), 0);  // 0.0, 5.0, -5.0
+        dmov_if_nz(b & kBitDoAcc, e.acc, acc_a);
+        dmov_if_nz(b & kBitDoMaint, e.acc, acc_m);
+        dmov_if(snap, e.vx, e.cruise);
         if (m_acc && e.acc == 5.0) b &= ~kBitDoAcc;
         if (snap) b &= ~kBitDoMaint;
     }
@@ -220,9 +222,12 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
         const bool m_left = (b & kBitLeft) != 0;
         const bool m_right = (b & kBitRight) != 0;  // never set together with left_mode
         // adding +0.0 is the identity on every value steer can hold (it is never -0.0)
-        e.steer = dadd(e.steer, m_left ? K.k30dt : (m_right ? -K.k30dt : 0.0));
+        double inc = 0.0;
+        dmov_if(m_left, inc, K.k30dt); dmov_if(m_right, inc, -K.k30dt);
+        e.steer = dadd(e.steer, inc);
         const bool reached = (m_left && e.py <= ty) || (m_right && e.py >= ty);
-        if (reached) { e.steer = 0.0; b &= ~(kBitLeft | kBitRight); }
+        dset_if(reached, e.steer, 0.0);
+        if (reached) b &= ~(kBitLeft | kBitRight);
     }
     const double vdt = dmul(e.vx, dt);
     if (e.steer != 0.0) {
@@ -237,8 +242,9 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
         const double d0 = fabs(dsub(e.py, 1.25)), d1 = fabs(dsub(e.py, 3.75)), d2 = fabs(dsub(e.py, 6.25));
         lane = (d0 <= d1 && d0 <= d2) ? 1 : (d1 <= d2) ? 2 : 3;
         l1 = lane == 1; l2 = lane == 2;
-        fpx = sel_lane(l1, l2, e.opx[0], e.opx[1], e.opx[2]);
-        fiv = sel_lane(l1, l2, e.oiv[0], e.oiv[1], e.oiv[2]);
+        fpx = e.opx[2]; fiv = e.oiv[2];
+        dmov_if(l2, fpx, e.opx[1]); dmov_if(l2, fiv, e.oiv[1]);
+        dmov_if(l1, fpx, e.opx[0]); dmov_if(l1, fiv, e.oiv[0]);
     }
     e.bits = (b & ~(3u << HW_BITS_LANE_SHIFT)) | ((uint32_t)lane << HW_BITS_LANE_SHIFT);
 
@@ -250,7 +256,8 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
         const int held = e.slow ? lane : 0;  // lane of the held-back obstacle, 0 = none
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const double d = (held == k + 1) ? vdt : e.odt[k];  // v * dt
+            double d = dmul(e.oiv[k], dt);  // v * dt
+            dmov_if(held == k + 1, d, vdt);
             e.opx[k] = dsub(dadd(e.opx[k], d), vdt);
             e.orx[k] = dadd(e.orx[k], d);
         }
@@ -291,10 +298,12 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     dmov_if(l2, fpx, e.opx[1]); dmov_if(l2, fiv, e.oiv[1]);
     dmov_if(l1, fpx, e.opx[0]); dmov_if(l1, fiv, e.oiv[0]);
     {
-        double fvx = fiv, cr = e.vx;
-        dmov_if(e.slow, fvx, e.vx);
-        dmov_if(fpx > 10.0, cr, fvx);
-        dmov_if((fire & kBitDoMaint) != 0, e.cruise, cr);
+        // maintain(): cruise = velocity of the vehicle ahead in the lane, else the car's own.  An obstacle that was held
+        // back in the previous tick (e.slow) moved by fl(fl(x + vdt) - vdt) <= 10 from x < 10, so one that is ahead
+        // (fpx > 10) moved with its own init_vx.
+        double cr = e.vx;
+        dmov_if(fpx > 10.0, cr, fiv);
+        dmov_if_nz(fire & kBitDoMaint, e.cruise, cr);
     }
 
     // ---- collision test on the rects the previous tick left (:920-937) ----
@@ -330,8 +339,8 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
         const double vc = ceil(e.vx), cc = ceil(e.cruise);
         const bool snap = m_maint & (vc == cc);
         const double acc_m = __hiloint2double(snap ? 0 : ((vc <= cc) ? 0x40140000 : (int)0xC0140000), 0);  // 0.0, 5.0, -5.0
-        dmov_if(m_acc, e.acc, acc_a);
-        dmov_if(m_maint, e.acc, acc_m);
+        dmov_if_nz(b & kBitDoAcc, e.acc, acc_a);
+        dmov_if_nz(b & kBitDoMaint, e.acc, acc_m);
         dmov_if(snap, e.vx, e.cruise);
         if (m_acc & (e.acc == 5.0)) b &= ~kBitDoAcc;
         if (snap) b &= ~kBitDoMaint;
@@ -453,8 +462,6 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
     if (i < n) {
         SaEnv e;
         sa_load(e, S, i, n);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) e.odt[k] = dmul(e.oiv[k], dt);
         const uint64_t env_id = env_id0 + (uint64_t)i;
 
         // episode accounting (Monitor) lives outside the tick loop
@@ -527,8 +534,6 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                 acc_eps += 1; acc_len += el; acc_ret += er; acc_col += nc; acc_to += (ncol == 0) ? 1 : 0;
                 if (autoreset) {
                     sa_reset_env(e);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) e.odt[k] = dmul(e.oiv[k], dt);
                     was_reset = true; ncoll_step = 0; ret_milli_step = 0; len_step = 0;
                 }
             }
