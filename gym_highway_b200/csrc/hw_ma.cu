@@ -232,7 +232,7 @@ __device__ __forceinline__ void ma_tick(MaHead &h, double *sm_car, double *sm_ob
         for (int j = 0; j < kMaxA; ++j) if (j < A && j != a) na += rects_overlap(cax[a], cay[a], cax[j], cay[j]) ? 1 : 0;
         h.nc_obs += no; h.nc_agent += na;
         if (no + na > 0) { done |= 1u << a; rewards[a] = -250.0; }
-        else rewards[a] = dsub(ddiv(CAR(a, C_VX), 20.0), 1.0);
+        else rewards[a] = dsub(ddiv_const(CAR(a, C_VX), 20.0), 1.0);
     }
 }
 

@@ -518,7 +518,7 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
             const uint32_t tick = e.bits & HW_BITS_TICK_MASK;
             const bool timeout = tick >= (uint32_t)K.timeout_tick;
             is_done = timeout || ncol > 0;
-            reward = (ncol > 0) ? -250.0 * (double)ncol : dsub(ddiv(e.vx, 20.0), 1.0);
+            reward = (ncol > 0) ? -250.0 * (double)ncol : dsub(ddiv_const(e.vx, 20.0), 1.0);
             rew_milli = round_milli(reward);
             ret_milli_step += rew_milli;
             len_step += 1;
@@ -550,9 +550,9 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
         }
     }
     store_obs_warp(sm_tile, obs, warp_base, n);
-    if (stats) {  // all 32 lanes are here (warps entirely out of range returned at the top)
-        const long long eps = warp_sum(acc_eps);
-        if (eps != 0) {
+    if (stats && __any_sync(0xffffffffu, acc_eps != 0)) {  // all 32 lanes are here (warps entirely out of range returned at the top)
+        {
+            const long long eps = warp_sum(acc_eps);
             const long long len = warp_sum(acc_len), ret = warp_sum(acc_ret), col = warp_sum(acc_col), to = warp_sum(acc_to);
             if ((threadIdx.x & 31) == 0) {
                 atomicAdd(&stats[0], (unsigned long long)eps);
