@@ -16,6 +16,7 @@ FLAG_NO_INF_OBS = 2
 FLAG_NO_AUTORESET = 4
 FLAG_SHARED_REWARD = 16
 FLAG_EXACT_STEERING = 32
+FLAG_MA_THREAD_PER_ENV = 64
 MA_MAX_AGENTS = 5
 MA_MAX_SLOTS = 16
 

@@ -480,6 +480,7 @@ static int ma_launch_step(const HwMaState *st, const void *actions, const HwMaOu
     if (P->ticks_per_step < 1 || P->timeout_tick < 1 || P->timeout_tick > 0xFFFF || !(P->dt > 0.0)) return HW_E_BADARG;
     MaConsts C_;
     C_.dt = P->dt; C_.k30dt = 30.0 * P->dt; C_.ticks_per_step = P->ticks_per_step; C_.timeout_tick = P->timeout_tick;
+    if (!(flags & HW_FLAG_MA_THREAD_PER_ENV)) return ma_grp_launch_step(st, actions, out, C_, seed, env_id0, n, flags, stream);
     const size_t smem = ma_smem(st);
     const unsigned grid = (unsigned)((n + kMaBlock - 1) / kMaBlock);
 #define HW_MA_LAUNCH(C, E) do { \

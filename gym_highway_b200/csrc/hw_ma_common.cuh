@@ -1,5 +1,5 @@
-// Declarations shared by the two multi-agent step kernels (thread-per-environment: hw_ma.cu, eight lanes per
-// environment: hw_ma_oct.cu).
+// Declarations shared by the two multi-agent step kernels (thread per environment: hw_ma.cu, eight lanes per
+// environment: hw_ma_grp.cu).
 #pragma once
 #include "hw_common.cuh"
 #include "../../include/highway_b200.h"
@@ -75,8 +75,8 @@ __device__ __forceinline__ float norm_f64(double raw, const double lo, const dou
 }
 
 
-// eight lanes per environment (hw_ma_oct.cu)
-int ma_oct_launch_step(const HwMaState *st, const void *actions, const HwMaOut *out, const MaConsts &C,
+// G lanes per environment (hw_ma_grp.cu); arguments already validated by the caller
+int ma_grp_launch_step(const HwMaState *st, const void *actions, const HwMaOut *out, const MaConsts &C,
                        uint64_t seed, uint64_t env_id0, int64_t n, int flags, cudaStream_t stream);
 
 }  // namespace hw

@@ -43,6 +43,8 @@ extern "C" {
 #define HW_FLAG_SHARED_REWARD 16 /* multi-agent: every car receives the sum of the rewards (shared_reward=True) */
 #define HW_FLAG_EXACT_STEERING 32 /* evaluate vx / (4 / tan) with the reference's two divisions instead of vx*tan/4
                                     * (slower; floats then match the fp64 reference bit for bit after fp32 rounding) */
+#define HW_FLAG_MA_THREAD_PER_ENV 64 /* multi-agent step: use the one-thread-per-environment kernel instead of the default
+                                      * eight-lanes-per-environment kernel (same results; kept for comparison) */
 
 /* discrete actions, gym_highway/envs/highway_env.py:14-20 */
 #define HW_ACT_LEFT 0
