@@ -102,73 +102,99 @@ __device__ __forceinline__ void grp_publish(const GrpCar &c, const GrpSm<G> &sm,
 
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7FF0000000000000ll); }
 
-// one world.act() followed by Scenario.rewards(); `reward` is the lane's own, done bits are or-ed into `done`.
+// State of one lane during a step, and the stages of a tick (one world.act() followed by Scenario.rewards()).
+//
+// Control flow is uniform over the WARP: every lane walks through the same stages and the same full-mask
+// __syncwarp / __ballot_sync calls, and a group that has finished its step (or has no environment) simply has
+// `active` false.  (Group-mask collectives compile to a divergence check plus a slow path that the hardware takes
+// whenever the warp is not fully converged - always, with G = 5, where lanes 30 and 31 idle.)
 // AT = number of cars when known at compile time (5), 0 = read it from the state.  Lanes g >= A run the car code on a
-// dummy car (their slots in shared memory exist and are never read) so that the group stays converged; only memory
-// traffic to global memory and the counters are masked.
+// dummy car (their slots in shared memory exist and are never read) so that a group stays converged; only traffic
+// to global memory and the collision counters are masked.
 template <int G, int AT, bool CONT, bool EXACT>
-__device__ __forceinline__ void grp_tick(MaHead &h, GrpCar &c, const GrpSm<G> &sm, int &cur, const int g, const int A_rt, const int K,
-                                         const unsigned gmask, const MaConsts &C, const bool inf_obs,
-                                         const uint32_t amask, const uint32_t apair, const int dlane,
-                                         const double a0_5dt, const double a1_30dt, const uint64_t seed, const uint64_t env_id,
-                                         double &reward, uint32_t &done)
-{
+struct GrpStep {
     using LY = GrpLayout<G>;
-    constexpr int CS = LY::kEnvs * G;  // stride between fields
-    const int A = AT ? AT : A_rt;
-    const double dt = C.dt;
-    const bool is_car = g < A;
-    double *pc = sm.car + (size_t)sm.e * G;
-    int *pi = sm.ci + (size_t)sm.e * G;
-    h.tick += 1;
-    if (h.tick >= (uint32_t)C.timeout_tick) done |= (1u << A) - 1u;  // highway_core.py:276-277
+    static constexpr int CS = LY::kEnvs * G;  // stride between fields of the published arrays
+    MaHead h;
+    GrpCar c;
+    GrpSm<G> sm;
+    double *pc;
+    int *pi;
+    int g, base, A, K, cur;
+    bool active;
+    uint32_t done;
+    int no_acc, na_acc;   // this car's collisions during the step
+    double reward, ang;
+    int lead, last;
+    uint32_t amask, apair, fire;
+    int dlane;
+    double a0_5dt, a1_30dt;
 
-    // ---- actions for every car in id order (highway_core.py:280-281, :110-188) ----
-    if (CONT) {
-        c.acc = py_clamp(dadd(c.acc, a0_5dt), -5.0, 5.0);
-        c.steer = py_clamp(dadd(c.steer, a1_30dt), -30.0, 30.0);
-    } else {
+    __device__ __forceinline__ GrpStep(double *smem, int e, int g_, int base_, int A_, int K_)
+        : sm(smem, e), g(g_), base(base_), A(AT ? AT : A_), K(K_), cur(0), active(false), done(0), no_acc(0), na_acc(0),
+          reward(0.0), ang(0.0), lead(0), last(0), amask(0), apair(0), fire(0), dlane(0), a0_5dt(0.0), a1_30dt(0.0)
+    {
+        pc = sm.car + (size_t)e * G;
+        pi = sm.ci + (size_t)e * G;
+    }
+
+    __device__ __forceinline__ unsigned group_bits(unsigned ballot) const { return (ballot >> base) & ((1u << G) - 1u); }
+
+    // ---- actions for every car in id order (highway_core.py:280-281, :110-188), part 1: everything but maintain()'s search ----
+    __device__ __forceinline__ void actions(const MaConsts &C)
+    {
+        h.tick += 1;
+        if (h.tick >= (uint32_t)C.timeout_tick) done |= (1u << A) - 1u;  // highway_core.py:276-277
+        if (CONT) {
+            c.acc = py_clamp(dadd(c.acc, a0_5dt), -5.0, 5.0);
+            c.steer = py_clamp(dadd(c.steer, a1_30dt), -30.0, 30.0);
+            return;
+        }
         // amask = the mode bit the action asks for; it fires when not yet set.  The two modes of a pair exclude each
         // other, so setting the bit and clearing its partner is the identity when nothing fires.
         uint32_t b = c.b;
         int lane = car_lane(b);
-        pi[I_LANE_OLD * CS + g] = lane;
-        const uint32_t fire = amask & ~b;
+        const int lane_old = lane;
+        fire = amask & ~b;
         b = (b & ~apair) | amask;
         lane = (fire & (kBitLeft | kBitRight)) ? min(max(lane + dlane, 1), 3) : lane;
         c.acc = py_clamp(c.acc, -5.0, 5.0);
         c.steer = py_clamp(c.steer, -30.0, 30.0);
         c.b = with_lane(b, lane);
-        pi[I_LANE * CS + g] = lane;
-        __syncwarp(gmask);
-        if (fire & kBitDoMaint) {
-            // all_obstacles iterates the cars (id order) and then the obstacles (insertion order): nearest strictly
-            // ahead in the lane, first wins ties; cars before this one have already switched lanes, cars after it have not
-            double bpx = dinf(), bvx = c.vx;
-#pragma unroll
-            for (int j = 0; j < kMaxA; ++j) {
-                if (AT ? (j >= AT) : false) break;
-                const int lj = (j < g) ? pi[I_LANE * CS + j] : pi[I_LANE_OLD * CS + j];
-                const double opx = pc[P_PX * CS + j], ovx = pc[(P_VX0 + cur) * CS + j];
-                const bool take = (j < A) & (j != g) & (lj == lane) & (opx > c.px) & (opx < bpx);
-                dmov_if(take, bpx, opx); dmov_if(take, bvx, ovx);
-            }
-            for (int k = 0; k < (int)h.nobs; ++k) {
-                const double opx = sm.o(O_PX, k), ovx = sm.o(O_VX, k);
-                const bool take = (ob_lane(h, k) == lane) & (opx > c.px) & (opx < bpx);
-                dmov_if(take, bpx, opx); dmov_if(take, bvx, ovx);
-            }
-            c.cruise = bvx;
-        }
+        pi[I_LANE * CS + g] = lane | (lane_old << 8);  // both are needed by the other cars' maintain()
     }
 
-    // ---- car updates in id order against last tick's leader (agent.py:79-165) ----
-    const int L = (int)h.leader;
-    const int nxt = cur ^ 1;
-    double ang = 0.0;
+    // part 2, for the cars whose MAINTAIN fired: all_obstacles iterates the cars (id order) and then the obstacles
+    // (insertion order): nearest strictly ahead in the lane, first wins ties; cars before this one have already
+    // switched lanes, cars after it have not
+    __device__ __forceinline__ void maintain_search()
     {
+        const int lane = car_lane(c.b);
+        double bpx = dinf(), bvx = c.vx;
+#pragma unroll
+        for (int j = 0; j < kMaxA; ++j) {
+            if (AT ? (j >= AT) : false) break;
+            const int lw = pi[I_LANE * CS + j];
+            const int lj = (j < g) ? (lw & 3) : (lw >> 8);
+            const double opx = pc[P_PX * CS + j], ovx = pc[(P_VX0 + cur) * CS + j];
+            const bool take = (j < A) & (j != g) & (lj == lane) & (opx > c.px) & (opx < bpx);
+            dmov_if(take, bpx, opx); dmov_if(take, bvx, ovx);
+        }
+        for (int k = 0; k < (int)h.nobs; ++k) {
+            const double opx = sm.o(O_PX, k), ovx = sm.o(O_VX, k);
+            const bool take = (ob_lane(h, k) == lane) & (opx > c.px) & (opx < bpx);
+            dmov_if(take, bpx, opx); dmov_if(take, bvx, ovx);
+        }
+        c.cruise = bvx;
+    }
+
+    // ---- car updates in id order against last tick's leader (agent.py:79-165), part 1: velocity and steering ----
+    __device__ __forceinline__ void update_velocity(const MaConsts &C)
+    {
+        const double dt = C.dt;
         uint32_t b = c.b;
         if (!CONT) {
+            pi[I_LANE * CS + g] = car_lane(b);  // from here on only the current lane is read
             const bool m_acc = (b & kBitDoAcc) != 0, m_maint = (b & kBitDoMaint) != 0;  // never both
             double acc_a = dadd(c.acc, dt);
             dset_if(c.acc < 0.0, acc_a, 0.0);
@@ -193,13 +219,18 @@ __device__ __forceinline__ void grp_tick(MaHead &h, GrpCar &c, const GrpSm<G> &s
             dset_if(reached, c.steer, 0.0);
             if (reached) b &= ~(kBitLeft | kBitRight);
         }
+        ang = 0.0;
         if (c.steer != 0.0) ang = angular_velocity<EXACT>(c.vx, c.steer);
         if (!CONT) c.vy = ang;  // agent.py:144: velocity.y = angular_velocity (discrete update only)
         c.b = b;
-        pc[(P_VX0 + nxt) * CS + g] = c.vx;  // the leader's velocity "as it is now" for the cars after it
+        pc[(P_VX0 + (cur ^ 1)) * CS + g] = c.vx;  // the leader's velocity "as it is now" for the cars after it
     }
-    __syncwarp(gmask);
+
+    // part 2: positions, against the leader's new velocity for the cars after it in id order, its old one for those before
+    __device__ __forceinline__ void update_position(const MaConsts &C)
     {
+        const double dt = C.dt;
+        const int L = (int)h.leader, nxt = cur ^ 1;
         const double vdt = dmul(c.vx, dt);
         double px = dadd(c.px, vdt);
         double py = dadd(c.py, dmul(c.vy, dt));
@@ -217,37 +248,37 @@ __device__ __forceinline__ void grp_tick(MaHead &h, GrpCar &c, const GrpSm<G> &s
             c.b = with_lane(c.b, (d0 <= d1 && d0 <= d2) ? 1 : (d1 <= d2) ? 2 : 3);
         }
         grp_publish<G>(c, sm, g, nxt);
+        cur = nxt;
     }
-    cur = nxt;
-    __syncwarp(gmask);
 
-    // ---- obstacle updates (agent.py:223-260): yield to the nearest car ahead in the lane, by raw x ----
-    const double lvdt = dmul(pc[(P_VX0 + cur) * CS + L], dt);
-    for (int k = g; k < (int)h.nobs; k += G) {
-        const int lane = ob_lane(h, k);
-        const double orx = sm.o(O_RX, k), iv = sm.o(O_IV, k);
-        double bd = dinf(), bv = iv;
-#pragma unroll
-        for (int j = 0; j < kMaxA; ++j) {
-            if (AT ? (j >= AT) : false) break;
-            const double crx = pc[P_RX * CS + j], cvx = pc[(P_VX0 + cur) * CS + j];
-            const double d = dsub(crx, orx);
-            const bool take = (j < A) & (pi[I_LANE * CS + j] == lane) & (orx < crx) & (d < bd);  // first wins ties
-            dmov_if(take, bd, d); dmov_if(take, bv, cvx);
-        }
-        double v = py_clamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
-        dmov_if(bd < dinf(), v, iv);            // else min(init_vx, that car's vx)
-        dmov_if(bv < iv, v, bv);
-        const double odt = dmul(v, dt);
-        const double opx = dsub(dadd(sm.o(O_PX, k), odt), lvdt);
-        sm.o(O_VX, k) = v; sm.o(O_PX, k) = opx; sm.o(O_RX, k) = dadd(orx, odt);
-        sm.ox(k) = rect_x(opx);
-    }
-    h.ofresh = 0;  // every live obstacle has now written its rect
-
-    // ---- leader / last election: stable sort by x, descending (highway_core.py:294-297) ----
-    int lead = 0, last = 0;
+    // ---- obstacle updates (agent.py:223-260): yield to the nearest car ahead in the lane, by raw x; then the
+    //      leader / last election: stable sort by x, descending (highway_core.py:294-297) ----
+    __device__ __forceinline__ void obstacles_and_leader(const MaConsts &C)
     {
+        const double dt = C.dt;
+        const double lvdt = dmul(pc[(P_VX0 + cur) * CS + (int)h.leader], dt);
+        for (int k = g; k < (int)h.nobs; k += G) {
+            const int lane = ob_lane(h, k);
+            const double orx = sm.o(O_RX, k), iv = sm.o(O_IV, k);
+            double bd = dinf(), bv = iv;
+#pragma unroll
+            for (int j = 0; j < kMaxA; ++j) {
+                if (AT ? (j >= AT) : false) break;
+                const double crx = pc[P_RX * CS + j], cvx = pc[(P_VX0 + cur) * CS + j];
+                const double d = dsub(crx, orx);
+                const bool take = (j < A) & (pi[I_LANE * CS + j] == lane) & (orx < crx) & (d < bd);  // first wins ties
+                dmov_if(take, bd, d); dmov_if(take, bv, cvx);
+            }
+            double v = py_clamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
+            dmov_if(bd < dinf(), v, iv);            // else min(init_vx, that car's vx)
+            dmov_if(bv < iv, v, bv);
+            const double odt = dmul(v, dt);
+            const double opx = dsub(dadd(sm.o(O_PX, k), odt), lvdt);
+            sm.o(O_VX, k) = v; sm.o(O_PX, k) = opx; sm.o(O_RX, k) = dadd(orx, odt);
+            sm.ox(k) = rect_x(opx);
+        }
+        h.ofresh = 0;  // every live obstacle has now written its rect
+        lead = 0; last = 0;
         double plead = pc[P_PX * CS], plast = plead;
 #pragma unroll
         for (int j = 1; j < kMaxA; ++j) {
@@ -257,80 +288,82 @@ __device__ __forceinline__ void grp_tick(MaHead &h, GrpCar &c, const GrpSm<G> &s
             lead = up ? j : lead; dmov_if(up, plead, p);
             last = dn ? j : last; dmov_if(dn, plast, p);
         }
+        h.leader = (uint32_t)lead;
     }
-    h.leader = (uint32_t)lead;
-    __syncwarp(gmask);
 
-    if (inf_obs) {
-        // ---- spawn (highway_core.py:300-323) and retire (:327-342): rare, so detected by all lanes and carried out by lane 0 ----
+    // ---- spawn (highway_core.py:300-323) and retire (:327-342) are rare: every lane looks for the conditions ... ----
+    __device__ __forceinline__ bool spawn_retire_wanted(double &thr, double &last_rx) const
+    {
         bool want = false;
 #pragma unroll
         for (int lane = 0; lane < 3; ++lane) {
             const uint32_t s = h.newest[lane];
             want = want | ((s < 31u) & (sm.o(O_PX, (int)(s & 15u)) < -2.375));
         }
-        const double thr = dsub(dsub(-2.375, pc[P_PX * CS + lead]), 2.0);
-        const double last_rx = pc[P_RX * CS + last];
+        thr = dsub(dsub(-2.375, pc[P_PX * CS + lead]), 2.0);
+        last_rx = pc[P_RX * CS + last];
         for (int k = g; k < (int)h.nobs; k += G) want = want | (dsub(sm.o(O_RX, k), last_rx) < thr);
-        if (__any_sync(gmask, want)) {
-            if (g == 0) {
-                for (int lane = 0; lane < 3; ++lane) {
-                    const uint32_t s = h.newest[lane];
-                    if (s >= 31u) continue;  // the lane's newest obstacle was retired: the reference never spawns there again
-                    if (sm.o(O_PX, (int)s) < -2.375) {
-                        double u1, u2;
-                        spawn_uniforms(seed, env_id, h.spawn_ctr, u1, u2);
-                        h.spawn_ctr += 1;
-                        const double x = dadd(70.0, dmul(30.0, u1)), v = dadd(5.0, dmul(2.0, u2));
-                        const double ovx = sm.o(O_VX, (int)s);
-                        const double m = (ovx < v) ? ovx : v;  // min(rand_vel_x, obstacle.velocity.x): the old obstacle stays, slowed down
-                        sm.o(O_VX, (int)s) = m; sm.o(O_IV, (int)s) = m;
-                        if ((int)h.nobs < K) {
-                            const int nk = (int)h.nobs;
-                            sm.o(O_PX, nk) = x; sm.o(O_RX, nk) = dadd(pc[P_RX * CS + lead], dsub(x, pc[P_PX * CS + lead]));
-                            sm.o(O_VX, nk) = v; sm.o(O_IV, nk) = v;
-                            h.olane = (h.olane & ~(3u << (2 * nk))) | ((uint32_t)(lane + 1) << (2 * nk));
-                            h.ofresh |= 1u << nk;
-                            h.newest[lane] = (uint32_t)nk;
-                            h.nobs += 1;
-                        } else {
-                            h.flags |= 1u;  // out of slots: the spawn is dropped (tests require this never to happen)
-                        }
-                    }
+        return want;
+    }
+
+    // ... and lane 0 of the group does the serial slot bookkeeping
+    __device__ __forceinline__ void spawn_retire(const double thr, const double last_rx, const uint64_t seed, const uint64_t env_id)
+    {
+        for (int lane = 0; lane < 3; ++lane) {
+            const uint32_t s = h.newest[lane];
+            if (s >= 31u) continue;  // the lane's newest obstacle was retired: the reference never spawns there again
+            if (sm.o(O_PX, (int)s) < -2.375) {
+                double u1, u2;
+                spawn_uniforms(seed, env_id, h.spawn_ctr, u1, u2);
+                h.spawn_ctr += 1;
+                const double x = dadd(70.0, dmul(30.0, u1)), v = dadd(5.0, dmul(2.0, u2));
+                const double ovx = sm.o(O_VX, (int)s);
+                const double m = (ovx < v) ? ovx : v;  // min(rand_vel_x, obstacle.velocity.x): the old obstacle stays, slowed down
+                sm.o(O_VX, (int)s) = m; sm.o(O_IV, (int)s) = m;
+                if ((int)h.nobs < K) {
+                    const int nk = (int)h.nobs;
+                    sm.o(O_PX, nk) = x; sm.o(O_RX, nk) = dadd(pc[P_RX * CS + lead], dsub(x, pc[P_PX * CS + lead]));
+                    sm.o(O_VX, nk) = v; sm.o(O_IV, nk) = v;
+                    h.olane = (h.olane & ~(3u << (2 * nk))) | ((uint32_t)(lane + 1) << (2 * nk));
+                    h.ofresh |= 1u << nk;
+                    h.newest[lane] = (uint32_t)nk;
+                    h.nobs += 1;
+                } else {
+                    h.flags |= 1u;  // out of slots: the spawn is dropped (tests require this never to happen)
                 }
-                // order preserving compaction of what the last car has cleared
-                int w = 0;
-                uint32_t nl = 0, nf = 0, nn0 = 31u, nn1 = 31u, nn2 = 31u;
-                for (int k = 0; k < (int)h.nobs; ++k) {
-                    if (dsub(sm.o(O_RX, k), last_rx) < thr) continue;
-                    if (w != k) {
-                        sm.o(O_PX, w) = sm.o(O_PX, k); sm.o(O_RX, w) = sm.o(O_RX, k); sm.o(O_VX, w) = sm.o(O_VX, k); sm.o(O_IV, w) = sm.o(O_IV, k);
-                        sm.ox(w) = sm.ox(k);
-                    }
-                    nl |= (uint32_t)ob_lane(h, k) << (2 * w);
-                    nf |= ((h.ofresh >> k) & 1u) << w;
-                    if (h.newest[0] == (uint32_t)k) nn0 = (uint32_t)w;
-                    if (h.newest[1] == (uint32_t)k) nn1 = (uint32_t)w;
-                    if (h.newest[2] == (uint32_t)k) nn2 = (uint32_t)w;
-                    ++w;
-                }
-                h.nobs = (uint32_t)w; h.olane = nl; h.ofresh = nf; h.newest[0] = nn0; h.newest[1] = nn1; h.newest[2] = nn2;
             }
-            __syncwarp(gmask);
-            const int src = (int)(threadIdx.x & 31u) - g;  // lane 0 of the group
-            const uint32_t packed = h.nobs | (h.newest[0] << 8) | (h.newest[1] << 13) | (h.newest[2] << 18) | (h.flags << 24);
-            const uint32_t p = __shfl_sync(gmask, packed, src);
-            h.nobs = p & 31u; h.newest[0] = (p >> 8) & 31u; h.newest[1] = (p >> 13) & 31u; h.newest[2] = (p >> 18) & 31u; h.flags = p >> 24;
-            h.olane = __shfl_sync(gmask, h.olane, src);
-            h.ofresh = __shfl_sync(gmask, h.ofresh, src);
-            h.spawn_ctr = __shfl_sync(gmask, h.spawn_ctr, src);
         }
+        // order preserving compaction of what the last car has cleared
+        int w = 0;
+        uint32_t nl = 0, nf = 0, nn0 = 31u, nn1 = 31u, nn2 = 31u;
+        for (int k = 0; k < (int)h.nobs; ++k) {
+            if (dsub(sm.o(O_RX, k), last_rx) < thr) continue;
+            if (w != k) {
+                sm.o(O_PX, w) = sm.o(O_PX, k); sm.o(O_RX, w) = sm.o(O_RX, k); sm.o(O_VX, w) = sm.o(O_VX, k); sm.o(O_IV, w) = sm.o(O_IV, k);
+                sm.ox(w) = sm.ox(k);
+            }
+            nl |= (uint32_t)ob_lane(h, k) << (2 * w);
+            nf |= ((h.ofresh >> k) & 1u) << w;
+            if (h.newest[0] == (uint32_t)k) nn0 = (uint32_t)w;
+            if (h.newest[1] == (uint32_t)k) nn1 = (uint32_t)w;
+            if (h.newest[2] == (uint32_t)k) nn2 = (uint32_t)w;
+            ++w;
+        }
+        h.nobs = (uint32_t)w; h.olane = nl; h.ofresh = nf; h.newest[0] = nn0; h.newest[1] = nn1; h.newest[2] = nn2;
+    }
+
+    // header words lane 0 may have changed, as one 64-bit + two 32-bit values for the broadcast
+    __device__ __forceinline__ uint32_t pack_slots() const { return h.nobs | (h.newest[0] << 8) | (h.newest[1] << 13) | (h.newest[2] << 18) | (h.flags << 24); }
+    __device__ __forceinline__ void unpack_slots(uint32_t p)
+    {
+        h.nobs = p & 31u; h.newest[0] = (p >> 8) & 31u; h.newest[1] = (p >> 13) & 31u; h.newest[2] = (p >> 18) & 31u; h.flags = p >> 24;
     }
 
     // ---- Scenario.rewards -> check_collisions, after the updates and spawns of this tick (highway_core.py:401-422) ----
-    int no = 0, na = 0;
+    __device__ __forceinline__ bool collide()
     {
         const int ax = pi[I_RECTX * CS + g], ay = pi[I_RECTY * CS + g];
+        int no = 0, na = 0;
         for (int k = 0; k < (int)h.nobs; ++k) {
             const bool fresh = (h.ofresh >> k) & 1u;  // spawned in this tick: still pygame's default rect (0, 0, 76, 38)
             const int bx = fresh ? 0 : sm.ox(k);
@@ -342,203 +375,222 @@ __device__ __forceinline__ void grp_tick(MaHead &h, GrpCar &c, const GrpSm<G> &s
             if (AT ? (j >= AT) : false) break;
             na += ((j < A) & (j != g) & rects_overlap(ax, ay, pi[I_RECTX * CS + j], pi[I_RECTY * CS + j])) ? 1 : 0;
         }
+        const bool is_car = g < A;
         no = is_car ? no : 0; na = is_car ? na : 0;
+        no_acc += no; na_acc += na;
         reward = dsub(ddiv_const(c.vx, 20.0), 1.0);
         dset_if(no + na > 0, reward, -250.0);
+        return no + na > 0;
     }
-    h.nc_obs += (uint32_t)__reduce_add_sync(gmask, no);
-    h.nc_agent += (uint32_t)__reduce_add_sync(gmask, na);
-    const unsigned hit = __ballot_sync(gmask, no + na > 0);
-    done |= (hit >> ((threadIdx.x & 31u) - g)) & ((1u << A) - 1u);
-}
 
-// Scenario.observations (simple_base.py:82-154) + MultiAgentEnv._get_obs_norm (highway_env.py:139-149) of the lane's car
-template <int G>
-__device__ __forceinline__ void grp_observe(MaHead &h, const GrpCar &c, const GrpSm<G> &sm, const int cur, const int g, const int A,
-                                            float *__restrict__ ob /* this car's row of 4A+14 floats */)
-{
-    const int S = A + 2;
-    float2 *o2 = reinterpret_cast<float2 *>(ob);  // rows are 8-byte aligned: (4A+14)*4 bytes is a multiple of 8
-    o2[0] = make_float2(norm_f64(c.acc, -5.0, 5.0), norm_f64(c.steer, -30.0, 30.0));
-    o2[1] = make_float2(norm_f64(c.rx, 0.0, 1200.0), norm_f64(c.py, 0.0, 8.0));
-    o2[2 + S] = make_float2(norm_f64(c.vx, -20.0, 20.0), norm_f64(c.vy, -20.0, 20.0));
-    // other cars: slot j - (j > a)
-    for (int j = 0; j < A; ++j) {
-        if (j == g) continue;
-        const int s = j - (j > g ? 1 : 0);
-        o2[2 + s] = make_float2(norm_f64(dsub(sm.c(P_RX, j), c.rx), -60.0, 60.0), norm_f64(dsub(sm.c(P_PY, j), c.py), -8.0, 8.0));
-        o2[3 + S + s] = make_float2(norm_f64(dsub(sm.c(P_VX0 + cur, j), c.vx), -20.0, 20.0), norm_f64(dsub(sm.c(P_VY, j), c.vy), -20.0, 20.0));
-    }
-    // per lane the obstacle nearest in raw x (first wins ties, insertion order): slot A-1+lane
-    int near0 = -1, near1 = -1, near2 = -1;
-    double nd0 = 0.0, nd1 = 0.0, nd2 = 0.0;
-    for (int k = 0; k < (int)h.nobs; ++k) {
-        const int l = ob_lane(h, k);
-        const double d = fabs(dsub(c.rx, sm.o(O_RX, k)));
-        if (l == 1) { if (near0 < 0 || d < nd0) { near0 = k; nd0 = d; } }
-        else if (l == 2) { if (near1 < 0 || d < nd1) { near1 = k; nd1 = d; } }
-        else { if (near2 < 0 || d < nd2) { near2 = k; nd2 = d; } }
-    }
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-        const int s = A - 1 + l;
-        const int k = (l == 0) ? near0 : (l == 1) ? near1 : near2;
-        if (k < 0) {  // the reference raises here; flag it and emit the centre of the range
-            h.flags |= 2u;
-            o2[2 + s] = make_float2(0.5f, 0.5f); o2[3 + S + s] = make_float2(0.5f, 0.5f);
-            continue;
-        }
-        o2[2 + s] = make_float2(norm_f64(dsub(sm.o(O_RX, k), c.rx), -60.0, 60.0), norm_f64(dsub(lane_centre(l), c.py), -8.0, 8.0));
-        o2[3 + S + s] = make_float2(norm_f64(dsub(sm.o(O_VX, k), c.vx), -20.0, 20.0), norm_f64(dsub(0.0, c.vy), -20.0, 20.0));
-    }
-}
-
-template <int G>
-__device__ __forceinline__ void grp_load(MaHead &h, GrpCar &c, const GrpSm<G> &sm, const MaPtrs &S, const int g, const bool is_car,
-                                         const int64_t i, const int64_t n)
-{
-    ma_load_head(h, S, i, n);
-    if (is_car) {
-        const float *p = S.cars + (int64_t)(g * 9) * n + i;
-        c.px = (double)p[0]; c.py = (double)p[n]; c.rx = (double)p[2 * n]; c.vx = (double)p[3 * n]; c.vy = (double)p[4 * n];
-        c.acc = (double)p[5 * n]; c.steer = (double)p[6 * n]; c.cruise = (double)p[7 * n];
-        c.b = __float_as_uint(p[8 * n]);
-    }
-    for (int k = g; k < (int)h.nobs; k += G) {
-        const float4 o = S.obst[(int64_t)k * n + i];
-        sm.o(O_PX, k) = o.x; sm.o(O_RX, k) = o.y; sm.o(O_VX, k) = o.z; sm.o(O_IV, k) = o.w;
-        sm.ox(k) = rect_x((double)o.x);
-    }
-}
-
-template <int G>
-__device__ __forceinline__ void grp_store(const MaHead &h, const GrpCar &c, const GrpSm<G> &sm, const MaPtrs &S, const int g,
-                                          const bool is_car, const int64_t i, const int64_t n)
-{
-    if (g == 0) ma_store_head(h, S, i, n);
-    if (is_car) {
-        float *p = S.cars + (int64_t)(g * 9) * n + i;
-        p[0] = (float)c.px; p[n] = (float)c.py; p[2 * n] = (float)c.rx; p[3 * n] = (float)c.vx; p[4 * n] = (float)c.vy;
-        p[5 * n] = (float)c.acc; p[6 * n] = (float)c.steer; p[7 * n] = (float)c.cruise;
-        p[8 * n] = __uint_as_float(c.b);
-    }
-    for (int k = g; k < (int)h.nobs; k += G)
-        S.obst[(int64_t)k * n + i] = make_float4((float)sm.o(O_PX, k), (float)sm.o(O_RX, k), (float)sm.o(O_VX, k), (float)sm.o(O_IV, k));
-}
-
-template <int G>
-struct GrpIds {
-    int g, e;
-    int64_t i;
-    bool live;
-    unsigned gmask;
-    __device__ __forceinline__ GrpIds(int64_t n)
+    // Scenario.observations (simple_base.py:82-154) + MultiAgentEnv._get_obs_norm (highway_env.py:139-149) of the lane's car
+    __device__ __forceinline__ void observe(float *__restrict__ ob /* this car's row of 4A+14 floats */)
     {
-        using L = GrpLayout<G>;
-        const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int ew = lane_id / G;
-        g = lane_id - ew * G;
-        e = warp * L::kEnvsPerWarp + ew;
-        i = (int64_t)blockIdx.x * L::kEnvs + e;
-        live = ew < L::kEnvsPerWarp && i < n;
-        gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (ew * G));
+        const int S = A + 2;
+        float2 *o2 = reinterpret_cast<float2 *>(ob);  // rows are 8-byte aligned: (4A+14)*4 bytes is a multiple of 8
+        o2[0] = make_float2(norm_f64(c.acc, -5.0, 5.0), norm_f64(c.steer, -30.0, 30.0));
+        o2[1] = make_float2(norm_f64(c.rx, 0.0, 1200.0), norm_f64(c.py, 0.0, 8.0));
+        o2[2 + S] = make_float2(norm_f64(c.vx, -20.0, 20.0), norm_f64(c.vy, -20.0, 20.0));
+        // other cars: slot j - (j > a)
+#pragma unroll
+        for (int j = 0; j < kMaxA; ++j) {
+            if (AT ? (j >= AT) : false) break;
+            if (j >= A || j == g) continue;
+            const int s = j - (j > g ? 1 : 0);
+            o2[2 + s] = make_float2(norm_f64(dsub(pc[P_RX * CS + j], c.rx), -60.0, 60.0), norm_f64(dsub(pc[P_PY * CS + j], c.py), -8.0, 8.0));
+            o2[3 + S + s] = make_float2(norm_f64(dsub(pc[(P_VX0 + cur) * CS + j], c.vx), -20.0, 20.0), norm_f64(dsub(pc[P_VY * CS + j], c.vy), -20.0, 20.0));
+        }
+        // per lane the obstacle nearest in raw x (first wins ties, insertion order): slot A-1+lane
+        double nd0 = dinf(), nd1 = dinf(), nd2 = dinf();
+        double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, vx0 = 0.0, vx1 = 0.0, vx2 = 0.0;
+        for (int k = 0; k < (int)h.nobs; ++k) {
+            const int l = ob_lane(h, k);
+            const double orx = sm.o(O_RX, k), ovx = sm.o(O_VX, k);
+            const double d = fabs(dsub(c.rx, orx));
+            const bool t0 = (l == 1) & (d < nd0), t1 = (l == 2) & (d < nd1), t2 = (l == 3) & (d < nd2);
+            dmov_if(t0, nd0, d); dmov_if(t0, rx0, orx); dmov_if(t0, vx0, ovx);
+            dmov_if(t1, nd1, d); dmov_if(t1, rx1, orx); dmov_if(t1, vx1, ovx);
+            dmov_if(t2, nd2, d); dmov_if(t2, rx2, orx); dmov_if(t2, vx2, ovx);
+        }
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const int s = A - 1 + l;
+            const double nd = (l == 0) ? nd0 : (l == 1) ? nd1 : nd2;
+            const double orx = (l == 0) ? rx0 : (l == 1) ? rx1 : rx2, ovx = (l == 0) ? vx0 : (l == 1) ? vx1 : vx2;
+            float2 pos = make_float2(norm_f64(dsub(orx, c.rx), -60.0, 60.0), norm_f64(dsub(lane_centre(l), c.py), -8.0, 8.0));
+            float2 vel = make_float2(norm_f64(dsub(ovx, c.vx), -20.0, 20.0), norm_f64(dsub(0.0, c.vy), -20.0, 20.0));
+            if (!(nd < dinf())) {  // the reference raises here; flag it and emit the centre of the range
+                h.flags |= 2u;
+                pos = make_float2(0.5f, 0.5f); vel = make_float2(0.5f, 0.5f);
+            }
+            o2[2 + s] = pos; o2[3 + S + s] = vel;
+        }
+    }
+
+    __device__ __forceinline__ void load(const MaPtrs &S, const int64_t i, const int64_t n)
+    {
+        ma_load_head(h, S, i, n);
+        c.px = c.py = c.rx = c.vx = c.vy = c.acc = c.steer = c.cruise = 0.0; c.b = 0;
+        if (g < A) {
+            const float *p = S.cars + (int64_t)(g * 9) * n + i;
+            c.px = (double)p[0]; c.py = (double)p[n]; c.rx = (double)p[2 * n]; c.vx = (double)p[3 * n]; c.vy = (double)p[4 * n];
+            c.acc = (double)p[5 * n]; c.steer = (double)p[6 * n]; c.cruise = (double)p[7 * n];
+            c.b = __float_as_uint(p[8 * n]);
+        }
+        for (int k = g; k < (int)h.nobs; k += G) {
+            const float4 o = S.obst[(int64_t)k * n + i];
+            sm.o(O_PX, k) = o.x; sm.o(O_RX, k) = o.y; sm.o(O_VX, k) = o.z; sm.o(O_IV, k) = o.w;
+            sm.ox(k) = rect_x((double)o.x);
+        }
+        cur = 0;
+        grp_publish<G>(c, sm, g, cur);
+    }
+
+    __device__ __forceinline__ void store(const MaPtrs &S, const int64_t i, const int64_t n) const
+    {
+        if (g == 0) ma_store_head(h, S, i, n);
+        if (g < A) {
+            float *p = S.cars + (int64_t)(g * 9) * n + i;
+            p[0] = (float)c.px; p[n] = (float)c.py; p[2 * n] = (float)c.rx; p[3 * n] = (float)c.vx; p[4 * n] = (float)c.vy;
+            p[5 * n] = (float)c.acc; p[6 * n] = (float)c.steer; p[7 * n] = (float)c.cruise;
+            p[8 * n] = __uint_as_float(c.b);
+        }
+        for (int k = g; k < (int)h.nobs; k += G)
+            S.obst[(int64_t)k * n + i] = make_float4((float)sm.o(O_PX, k), (float)sm.o(O_RX, k), (float)sm.o(O_VX, k), (float)sm.o(O_IV, k));
     }
 };
 
+#ifndef HW_MA_MIN_BLOCKS
+#define HW_MA_MIN_BLOCKS 3
+#endif
+
 template <int G, int AT, bool CONT, bool EXACT>
-__global__ void __launch_bounds__(kGrpWarps * 32, 3)
+__global__ void __launch_bounds__(kGrpWarps * 32, HW_MA_MIN_BLOCKS)
 ma_grp_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew,
                    uint8_t *__restrict__ done_out, double *__restrict__ term, unsigned long long *__restrict__ stats,
                    const MaConsts C, const uint64_t seed, const uint64_t env_id0, const int64_t n, const int flags)
 {
+    using LY = GrpLayout<G>;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ double sm_dyn[];
-    const GrpIds<G> id(n);
-    const int g = id.g, A = AT ? AT : S.A, K = S.K, D = 4 * A + 14;
-    const unsigned gmask = id.gmask;
-    const int64_t i = id.i;
+    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ew = lane_id / G;                      // environment within the warp (ew == kEnvsPerWarp: idle lane)
+    const int g = lane_id - ew * G;
+    const bool has_env = ew < LY::kEnvsPerWarp;
+    const int e = has_env ? warp * LY::kEnvsPerWarp + ew : 0;
+    const int64_t i = (int64_t)blockIdx.x * LY::kEnvs + e;
+    const bool live = has_env && i < n;
+    GrpStep<G, AT, CONT, EXACT> st(sm_dyn, e, g, ew * G, S.A, S.K);
+    const int A = st.A, D = 4 * A + 14;
+    const bool is_car = g < A;
+    const bool inf_obs = !(flags & HW_FLAG_NO_INF_OBS);
+    const bool autoreset = !(flags & HW_FLAG_NO_AUTORESET);
+    const bool shared_reward = (flags & HW_FLAG_SHARED_REWARD) != 0;
+    const uint64_t env_id = env_id0 + (uint64_t)i;
     long long acc[7] = {0, 0, 0, 0, 0, 0, 0};  // finished episode of this group (lane 0), summed per warp at the end
-    if (id.live) {
-        const GrpSm<G> sm(sm_dyn, id.e);
-        const bool is_car = g < A;
-        const bool inf_obs = !(flags & HW_FLAG_NO_INF_OBS);
-        const bool autoreset = !(flags & HW_FLAG_NO_AUTORESET);
-        const bool shared_reward = (flags & HW_FLAG_SHARED_REWARD) != 0;
-        MaHead h;
-        GrpCar c;
-        c.px = c.py = c.rx = c.vx = c.vy = c.acc = c.steer = c.cruise = 0.0; c.b = 0;
-        grp_load<G>(h, c, sm, S, g, is_car, i, n);
-        int cur = 0;
-        if (is_car) grp_publish<G>(c, sm, g, cur);
-        uint32_t amask = 0, apair = 0;
-        int dlane = 0;
-        double a0_5dt = 0.0, a1_30dt = 0.0;
+
+    if (live) {
+        st.load(S, i, n);
         if (is_car) {
             if (CONT) {
                 const float2 v = reinterpret_cast<const float2 *>(actions)[i * A + g];
-                a0_5dt = dmul(dmul((double)v.x, 5.0), C.dt);
-                a1_30dt = dmul(dmul((double)v.y, 30.0), C.dt);
+                st.a0_5dt = dmul(dmul((double)v.x, 5.0), C.dt);
+                st.a1_30dt = dmul(dmul((double)v.y, 30.0), C.dt);
             } else {
                 const int act = reinterpret_cast<const int *>(actions)[i * A + g];
-                amask = (act == HW_ACT_LEFT) ? kBitLeft : (act == HW_ACT_RIGHT) ? kBitRight
-                      : (act == HW_ACT_ACCELERATE) ? kBitDoAcc : (act == HW_ACT_MAINTAIN) ? kBitDoMaint : 0u;
-                apair = (amask & (kBitLeft | kBitRight)) ? (kBitLeft | kBitRight) : amask ? (kBitDoAcc | kBitDoMaint) : 0u;
-                dlane = (act == HW_ACT_RIGHT) ? 1 : (act == HW_ACT_LEFT) ? -1 : 0;
+                st.amask = (act == HW_ACT_LEFT) ? kBitLeft : (act == HW_ACT_RIGHT) ? kBitRight
+                         : (act == HW_ACT_ACCELERATE) ? kBitDoAcc : (act == HW_ACT_MAINTAIN) ? kBitDoMaint : 0u;
+                st.apair = (st.amask & (kBitLeft | kBitRight)) ? (kBitLeft | kBitRight) : st.amask ? (kBitDoAcc | kBitDoMaint) : 0u;
+                st.dlane = (act == HW_ACT_RIGHT) ? 1 : (act == HW_ACT_LEFT) ? -1 : 0;
             }
         }
-        __syncwarp(gmask);
+    }
+    st.active = live;
+    __syncwarp();
 
-        double r = 0.0;
-        uint32_t done = 0;
-        for (int t = 0; t < C.ticks_per_step; ++t) {
-            grp_tick<G, AT, CONT, EXACT>(h, c, sm, cur, g, A, K, gmask, C, inf_obs, amask, apair, dlane, a0_5dt, a1_30dt, seed, env_id0 + (uint64_t)i, r, done);
-            if (done) break;  // highway_env.py:85-86
+    for (int t = 0; t < C.ticks_per_step; ++t) {
+        if (__ballot_sync(FULL, st.active) == 0u) break;
+        if (st.active) st.actions(C);
+        if (!CONT) {
+            __syncwarp();
+            if (st.active && (st.fire & kBitDoMaint)) st.maintain_search();
         }
-        // rewards of the step: summed in id order for shared_reward (highway_env.py:92-94) and for Monitor
-        if (is_car) sm.r(g) = r;
-        __syncwarp(gmask);
-        double rsum = 0.0;
-        for (int a = 0; a < A; ++a) { const double ra = sm.r(a); rsum = dadd(rsum, ra); }
+        if (st.active) st.update_velocity(C);
+        __syncwarp();
+        if (st.active) st.update_position(C);
+        __syncwarp();
+        if (st.active) st.obstacles_and_leader(C);
+        __syncwarp();
+        if (inf_obs) {
+            double thr = 0.0, last_rx = 0.0;
+            const bool want = st.active && st.spawn_retire_wanted(thr, last_rx);
+            const unsigned wanted = __ballot_sync(FULL, want);
+            if (wanted) {  // some group of the warp has an obstacle to spawn or to retire
+                const bool mine = st.group_bits(wanted) != 0u;
+                if (mine && g == 0) st.spawn_retire(thr, last_rx, seed, env_id);
+                __syncwarp();
+                const uint32_t p = __shfl_sync(FULL, st.pack_slots(), ew * G);
+                const uint32_t ol = __shfl_sync(FULL, st.h.olane, ew * G), of = __shfl_sync(FULL, st.h.ofresh, ew * G);
+                const uint32_t sc = __shfl_sync(FULL, st.h.spawn_ctr, ew * G);
+                if (mine) { st.unpack_slots(p); st.h.olane = ol; st.h.ofresh = of; st.h.spawn_ctr = sc; }
+            }
+        }
+        const bool hit = st.active && st.collide();
+        const unsigned hits = st.group_bits(__ballot_sync(FULL, hit));
+        if (st.active) {
+            st.done |= hits & ((1u << A) - 1u);
+            if (st.done) st.active = false;  // highway_env.py:85-86: the step ends with the first tick that finishes a car
+        }
+    }
+
+    // rewards of the step: summed in id order for shared_reward (highway_env.py:92-94) and for Monitor; collision counters
+    if (live) { st.sm.r(g) = st.reward; st.pi[I_RECTX * st.CS + g] = st.no_acc; st.pi[I_RECTY * st.CS + g] = st.na_acc; }
+    __syncwarp();
+    if (live) {
+        double r = st.reward, rsum = 0.0;
+        for (int a = 0; a < A; ++a) {
+            rsum = dadd(rsum, st.sm.r(a));
+            st.h.nc_obs += (uint32_t)st.pi[I_RECTX * st.CS + a]; st.h.nc_agent += (uint32_t)st.pi[I_RECTY * st.CS + a];
+        }
         if (shared_reward) {
             r = rsum;
-            for (int a = 0; a < A; ++a) h.ep_ret = dadd(h.ep_ret, rsum);
+            for (int a = 0; a < A; ++a) st.h.ep_ret = dadd(st.h.ep_ret, rsum);
         } else {
-            for (int a = 0; a < A; ++a) h.ep_ret = dadd(h.ep_ret, sm.r(a));  // Monitor sums the python floats of every agent and step
+            for (int a = 0; a < A; ++a) st.h.ep_ret = dadd(st.h.ep_ret, st.sm.r(a));  // Monitor sums the python floats of every agent and step
         }
         if (is_car) {
             rew[i * A + g] = (float)r;
-            done_out[i * A + g] = (done >> g) & 1u;
+            done_out[i * A + g] = (st.done >> g) & 1u;
         }
-        h.ep_len += 1;
-
-        if (done) {
-            if (g == 0) {
-                if (term) {
-                    double *tm = term + 5 * i;
-                    tm[0] = (double)h.tick; tm[1] = (double)h.nc_obs; tm[2] = (double)h.nc_agent; tm[3] = h.ep_ret; tm[4] = (double)h.ep_len;
-                }
-                acc[0] = 1; acc[1] = h.ep_len; acc[2] = __double2ll_rn(h.ep_ret * 1000.0); acc[3] = h.nc_obs;
-                acc[4] = (h.tick >= (uint32_t)C.timeout_tick) ? 1 : 0; acc[5] = h.nc_agent; acc[6] = h.flags & 1u;
+        st.h.ep_len += 1;
+        if (st.done && g == 0) {
+            if (term) {
+                double *tm = term + 5 * i;
+                tm[0] = (double)st.h.tick; tm[1] = (double)st.h.nc_obs; tm[2] = (double)st.h.nc_agent; tm[3] = st.h.ep_ret; tm[4] = (double)st.h.ep_len;
             }
-            if (autoreset) {
-                const uint32_t keep = h.flags;
-                __syncwarp(gmask);  // every lane has finished reading the terminal state
-                grp_reset_env<G>(h, c, sm, g, is_car);
-                h.flags = keep;  // sticky diagnostics survive the reset
-                cur = 0;
-                if (is_car) grp_publish<G>(c, sm, g, cur);
-                for (int k = g; k < 3; k += G) sm.ox(k) = 0;
-                __syncwarp(gmask);
-            }
+            acc[0] = 1; acc[1] = st.h.ep_len; acc[2] = __double2ll_rn(st.h.ep_ret * 1000.0); acc[3] = st.h.nc_obs;
+            acc[4] = (st.h.tick >= (uint32_t)C.timeout_tick) ? 1 : 0; acc[5] = st.h.nc_agent; acc[6] = st.h.flags & 1u;
         }
-        if (is_car) grp_observe<G>(h, c, sm, cur, g, A, obs + (i * A + g) * (int64_t)D);
+    }
+    __syncwarp();  // every lane has finished reading the terminal state
+    if (live && st.done && autoreset) {
+        const uint32_t keep = st.h.flags;
+        grp_reset_env<G>(st.h, st.c, st.sm, g, is_car);
+        st.h.flags = keep;  // sticky diagnostics survive the reset
+        st.cur = 0;
+        grp_publish<G>(st.c, st.sm, g, st.cur);
+    }
+    __syncwarp();
+    if (live) {
+        if (is_car) st.observe(obs + (i * A + g) * (int64_t)D);
         // a lane without an obstacle to observe is the same finding for every car; the header is stored by lane 0 (always a car)
-        grp_store<G>(h, c, sm, S, g, is_car, i, n);
+        st.store(S, i, n);
     }
     if (stats) {
-        if (__any_sync(0xffffffffu, acc[0] != 0)) {
+        if (__any_sync(FULL, acc[0] != 0)) {
 #pragma unroll
             for (int j = 0; j < 7; ++j) acc[j] = warp_sum(acc[j]);
-            if ((threadIdx.x & 31) == 0) {
+            if (lane_id == 0) {
 #pragma unroll
                 for (int j = 0; j < 7; ++j) atomicAdd(&stats[j], (unsigned long long)acc[j]);
             }
@@ -549,7 +601,10 @@ ma_grp_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
 int ma_grp_launch_step(const HwMaState *st, const void *actions, const HwMaOut *out, const MaConsts &C_,
                        uint64_t seed, uint64_t env_id0, int64_t n, int flags, cudaStream_t stream)
 {
-    constexpr int G = 8;
+#ifndef HW_MA_GROUP
+#define HW_MA_GROUP 5
+#endif
+    constexpr int G = HW_MA_GROUP;
     using L = GrpLayout<G>;
     MaPtrs S;
     S.cars = st->cars; S.obst = reinterpret_cast<float4 *>(st->obst); S.head = st->head; S.A = st->num_agents; S.K = st->num_slots;
