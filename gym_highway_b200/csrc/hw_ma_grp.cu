@@ -31,37 +31,41 @@ template <int G>
 struct GrpLayout {
     static constexpr int kEnvsPerWarp = 32 / G;
     static constexpr int kEnvs = kEnvsPerWarp * kGrpWarps;  // environments per block
-    static constexpr int kRounds = (kMaxK + G - 1) / G;      // obstacle slots per lane
-    // published car fields (doubles): px, py, rx, vy, vx[2] (double buffered); ints: lane_old, lane, rect x, rect y
-    static constexpr int kCarD = 6, kCarI = 4;
-    static constexpr size_t kDoubles = (size_t)(kCarD + 1) * kEnvs * G + (size_t)O_NF * kRounds * kEnvs * G;
-    static constexpr size_t kInts = (size_t)kCarI * kEnvs * G + (size_t)kRounds * kEnvs * G;
+    // published car fields (doubles): px, py, rx, vy, vx[2] (double buffered); ints: lane (old << 8 | new), rect x, rect y
+    static constexpr int kCarD = 6, kCarI = 3;
+    // obstacle slots of one environment are contiguous (slot k of field f at ob[f][e * kObStride + k]): the loops that
+    // walk the list index with one add; the odd stride keeps the groups of a warp on different banks
+    static constexpr int kObStride = kMaxK + 1;
+    static constexpr size_t kDoubles = (size_t)(kCarD + 1) * kEnvs * G + (size_t)O_NF * kEnvs * kObStride;
+    static constexpr size_t kInts = (size_t)kCarI * kEnvs * G + (size_t)kEnvs * kObStride;
     static constexpr size_t kBytes = kDoubles * sizeof(double) + kInts * sizeof(int);
 };
 
 enum { P_PX = 0, P_PY, P_RX, P_VY, P_VX0, P_VX1 };
-enum { I_LANE_OLD = 0, I_LANE, I_RECTX, I_RECTY };
+enum { I_LANE = 0, I_RECTX, I_RECTY };
 
 template <int G>
 struct GrpSm {
     using L = GrpLayout<G>;
+    static constexpr int OS = L::kEnvs * L::kObStride;  // stride between obstacle fields
     double *car, *ob, *rew;
     int *ci, *obx;
     int e;  // environment within the block
     __device__ __forceinline__ GrpSm(double *base, int e_) : e(e_)
     {
         car = base;
-        ob = car + (size_t)L::kCarD * L::kEnvs * G;
-        rew = ob + (size_t)O_NF * L::kRounds * L::kEnvs * G;
+        double *ob0 = car + (size_t)L::kCarD * L::kEnvs * G;
+        rew = ob0 + (size_t)O_NF * OS;
         ci = reinterpret_cast<int *>(rew + (size_t)L::kEnvs * G);
-        obx = ci + (size_t)L::kCarI * L::kEnvs * G;
+        int *obx0 = ci + (size_t)L::kCarI * L::kEnvs * G;
+        ob = ob0 + e * L::kObStride;
+        obx = obx0 + e * L::kObStride;
     }
     __device__ __forceinline__ double &c(int f, int a) const { return car[((size_t)f * L::kEnvs + e) * G + a]; }
     __device__ __forceinline__ int &i(int f, int a) const { return ci[((size_t)f * L::kEnvs + e) * G + a]; }
     __device__ __forceinline__ double &r(int a) const { return rew[(size_t)e * G + a]; }
-    // obstacle slot k lives with lane k % G, round k / G
-    __device__ __forceinline__ double &o(int f, int k) const { return ob[(((size_t)f * L::kRounds + k / G) * L::kEnvs + e) * G + (k % G)]; }
-    __device__ __forceinline__ int &ox(int k) const { return obx[((size_t)(k / G) * L::kEnvs + e) * G + (k % G)]; }
+    __device__ __forceinline__ double &o(int f, int k) const { return ob[f * OS + k]; }
+    __device__ __forceinline__ int &ox(int k) const { return obx[k]; }
 };
 
 struct GrpCar {  // the lane's own car, registers
