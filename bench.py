@@ -329,7 +329,7 @@ def main():
                        "parallelism": "independent env shards, %d rank(s), no data-path collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(info["kind"], info["continuous"], n), "peak_source": peak_src,
-                         "kernel": "sa_step_kernel" if info["kind"] == "sa" else "ma_step_kernel",
+                         "kernel": "sa_step_kernel" if info["kind"] == "sa" else "ma_grp_step_kernel",
                          "algorithmic_bytes_per_env_step": bps,
                          "avg_launch_us": avg_launch_s * 1e6, "min_launch_us": float(dev_ms.min()) * 1e3},
             "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
