@@ -30,11 +30,49 @@ class MlpPolicy(nn.Module):
 
     def forward(self, obs):
         if self.bf16_inference and obs.is_cuda and not torch.is_grad_enabled():
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                h = self.body(obs)
-                return self.pi(h).float(), self.vf(h).float().squeeze(-1)
+            return self._forward_bf16(obs)
         h = self.body(obs)
         return self.pi(h), self.vf(h).squeeze(-1)
+
+    def _bf16_weights(self):
+        """bf16 copies of the weights for rollout-time inference, rebuilt when a parameter has been updated in place.
+        The input width (18) and the merged head width (n_out + 1) are zero-padded to multiples of 8 so that cuBLASLt
+        picks its aligned tensor-core kernels (the unaligned fallbacks are 3x slower at 10^5 rows)."""
+        ver = tuple(p._version for p in self.parameters())
+        if getattr(self, "_bf16_ver", None) != ver:
+            lin = [m for m in self.body if isinstance(m, nn.Linear)]
+            body = []
+            for k, m in enumerate(lin):
+                w = m.weight.detach().to(torch.bfloat16).t().contiguous()  # [in, out]
+                if k == 0 and w.shape[0] % 8:
+                    w = torch.cat([w, w.new_zeros(8 - w.shape[0] % 8, w.shape[1])], 0).contiguous()
+                body.append((w, m.bias.detach().to(torch.bfloat16)))
+            self._bf16_body = body
+            hw = torch.cat([self.pi.weight, self.vf.weight], 0).detach().to(torch.bfloat16)   # [n_out + 1, hidden]
+            hb = torch.cat([self.pi.bias, self.vf.bias], 0).detach().to(torch.bfloat16)
+            self._n_head = hw.shape[0]
+            if hw.shape[0] % 8:
+                pad = 8 - hw.shape[0] % 8
+                hw = torch.cat([hw, hw.new_zeros(pad, hw.shape[1])], 0)
+                hb = torch.cat([hb, hb.new_zeros(pad)], 0)
+            self._bf16_head_w, self._bf16_head_b = hw.t().contiguous(), hb
+            self._bf16_ver = ver
+        return self._bf16_body, self._bf16_head_w, self._bf16_head_b
+
+    def _forward_bf16(self, obs):
+        """rollout-time forward: one cuBLASLt GEMM per layer with the bias + ReLU epilogue fused (no separate
+        elementwise passes over the [N, 256] activations, which at 10^5 rows cost more than the GEMMs), heads merged"""
+        body, hw, hb = self._bf16_weights()
+        k0 = body[0][0].shape[0]
+        if obs.shape[1] == k0:
+            h = obs.to(torch.bfloat16)
+        else:
+            h = obs.new_zeros((obs.shape[0], k0), dtype=torch.bfloat16)
+            h[:, :obs.shape[1]] = obs
+        for w, b in body:
+            h = torch._addmm_activation(b, h, w, use_gelu=False)
+        out = torch.addmm(hb, h, hw).float()
+        return out[:, :self._n_head - 1], out[:, self._n_head - 1]
 
     @torch.no_grad()
     def step(self, obs, generator=None):
@@ -47,8 +85,14 @@ class MlpPolicy(nn.Module):
             return a.clamp(-1, 1), v, neglogp
         logp = torch.log_softmax(out, dim=-1)
         # categorical sample by inverse CDF on one uniform per env (cheaper than torch.multinomial at 10^5..10^6 rows)
-        u = torch.rand(out.shape[0], 1, device=out.device, generator=generator)
-        a = (logp.exp().cumsum(-1) < u).sum(-1).clamp_(max=out.shape[-1] - 1)
+        # (running sums over the handful of actions are spelled out: torch.cumsum over a last dimension of 4 costs 0.7 ms at 131k rows)
+        u = torch.rand(out.shape[0], device=out.device, generator=generator)
+        p = logp.exp()
+        c = p[:, 0]
+        a = (c < u).to(torch.int64)
+        for k in range(1, out.shape[-1] - 1):
+            c = c + p[:, k]
+            a += c < u
         return a.to(torch.int32), v, -logp.gather(-1, a.unsqueeze(-1)).squeeze(-1)
 
     @torch.no_grad()

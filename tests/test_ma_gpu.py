@@ -42,13 +42,14 @@ def _same_bits(name, got, want):
     assert nbad == 0, "%s: %d of %d values differ in the last bits" % (name, nbad, got.size)
 
 
+@pytest.mark.parametrize("kernel", ["group", "thread"])  # five lanes per environment (default) / one thread per environment
 @pytest.mark.parametrize("name", MA_GOLDEN)
-def test_golden_transitions(name):
+def test_golden_transitions(name, kernel):
     g = load_golden(name)
     A, K = int(g["num_agents"]), int(g["num_slots"])
     n = len(g["env_id"])
     env = _env(n, A, continuous=bool(g["continuous"]), seed=int(g["seed"]), env_id0=0, auto_reset=False,
-               shared_reward=bool(g["shared_reward"]), num_slots=K, exact_steering=True,
+               shared_reward=bool(g["shared_reward"]), num_slots=K, exact_steering=True, kernel=kernel,
                world_config=dict(real_time=bool(g["real_time"]), inf_obs=bool(g.get("inf_obs", True))))
     _load_state(env, ma_state_from_golden(g))
     obs, rew, done, _ = env.step(torch.from_numpy(np.ascontiguousarray(g["action"])).cuda())
@@ -64,10 +65,11 @@ def test_golden_transitions(name):
     assert int(env.diagnostics().max()) == 0
 
 
-@pytest.mark.parametrize("A,continuous", [(5, False), (5, True), (3, False), (1, True)])
-def test_trajectory_parity(A, continuous):
-    n, steps, seed = 2048, 400, 9
-    env = _env(n, A, continuous=continuous, seed=seed, env_id0=7, exact_steering=True)
+@pytest.mark.parametrize("A,continuous,kernel", [(5, False, "group"), (5, True, "group"), (3, False, "group"), (1, True, "group"),
+                                                 (4, False, "group"), (2, True, "group"), (5, False, "thread")])
+def test_trajectory_parity(A, continuous, kernel):
+    n, steps, seed = 2048 if kernel == "group" else 1000, 400, 9
+    env = _env(n, A, continuous=continuous, seed=seed, env_id0=7, exact_steering=True, kernel=kernel)
     st = mo.MaState(n, A)
     mo.ma_reset(st)
     rng = np.random.RandomState(2)
