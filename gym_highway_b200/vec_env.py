@@ -313,7 +313,7 @@ class HighwayVecEnv(VecEnv):
                                            _as_ptr(h['done']), C.byref(self.params), self._seed, self._env_id0,
                                            n, self._flags, self._stream())
         _lib.check(rc, "hw_sa_step_host")
-        return h['obs'].numpy(), h['rew'].numpy(), h['done'].numpy().astype(bool)
+        return h['obs'].numpy(), h['rew'].numpy(), h['done'].numpy().view(np.bool_)  # the kernel writes 0 / 1
 
     # ------------------------------------------------------------------ infos / statistics
     def _make_info_fetcher(self, out):

@@ -169,7 +169,7 @@ class HighwayMAVecEnv(VecEnv):
                                            _as_ptr(h['done']), C.byref(self.params), self._seed, self._env_id0,
                                            n, self._flags, self._stream())
         _lib.check(rc, "hw_ma_step_host")
-        return h['obs'].numpy(), h['rew'].numpy(), h['done'].numpy().astype(bool)
+        return h['obs'].numpy(), h['rew'].numpy(), h['done'].numpy().view(np.bool_)
 
     def _make_info_fetcher(self, out):
         def fetch(episodes_only):
