@@ -154,16 +154,21 @@ def test_vecenv_contract():
     env.close(); env.close()
 
 
-def test_host_buffer_step_matches_device_step():
-    n = 513
-    a, b = _env(n, seed=2), _env(n, seed=2)
+@pytest.mark.parametrize("n,steps,continuous", [(513, 20, False), (262144 + 77, 6, False), (300001, 4, True)])
+def test_host_buffer_step_matches_device_step(n, steps, continuous):
+    """hw_sa_step_host (host buffers; large batches run as two overlapped sub-range launches) against the device step"""
+    a, b = _env(n, seed=2, continuous=continuous), _env(n, seed=2, continuous=continuous)
     rng = np.random.RandomState(0)
-    for t in range(20):
-        act = rng.randint(0, 4, n).astype(np.int32)
+    a.rollout_random(40); b.rollout_random(40)  # respawns, lane changes and finished episodes in every chunk
+    for t in range(steps):
+        act = rng.uniform(-1, 1, (n, 2)).astype(np.float32) if continuous else rng.randint(0, 4, n).astype(np.int32)
         o1, r1, d1, _ = a.step(torch.from_numpy(act).cuda())
         o2, r2, d2 = b.step_host(act)
         assert bits_equal(o1.cpu().numpy(), o2) and bits_equal(r1.cpu().numpy(), r2)
         assert np.array_equal(d1.cpu().numpy(), d2)
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
 
 
 def test_rollout_random_is_deterministic_and_sane():
