@@ -175,3 +175,33 @@ class Runner(object):
         returns, _ = gae(self.mb_rewards, self.mb_values, self.mb_dones, last_values, self.dones, self.gamma, self.lam)
         return (sf01(self.mb_obs), sf01(returns), sf01(self.mb_dones), sf01(self.mb_actions), sf01(self.mb_values),
                 sf01(self.mb_neglogpacs), None, epinfos)
+
+    @torch.no_grad()
+    def run_graphed(self):
+        """`run(want_epinfos=False)` replayed from ONE CUDA graph holding the whole rollout (nsteps x (policy forward,
+        sampling, buffer writes, env step kernel) + GAE + sf01).  Eagerly a step is ~45 small launches and the host
+        cannot issue them as fast as the GPU retires them at 10^5 envs; the graph removes that bound.  The first call
+        captures (after one eager rollout as warm-up); the returned tensors live in the graph's memory pool and are
+        overwritten by the next call.  Episode statistics come from `env.episode_statistics()` (device counters);
+        per-episode infos are not available on this path.  nsteps must be even (the env alternates two output
+        buffers, and a replay has to start on the one the capture started on)."""
+        if self.nsteps % 2:
+            raise ValueError("run_graphed needs an even nsteps")
+        if getattr(self, "_graph", None) is None:
+            if self.generator is not None:
+                raise ValueError("run_graphed samples from the default CUDA generator (it is the one graph capture tracks); construct the Runner with generator=None")
+            self.run(want_epinfos=False)  # warm-up: cuBLAS workspaces, allocator pools
+            # the env hands out its own output buffer: keep private copies so that replays start from well-defined tensors
+            self._g_obs = self.obs.clone()
+            self._g_dones = self.dones.clone()
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.obs, self.dones = self._g_obs, self._g_dones
+                out = self.run(want_epinfos=False)
+                self._g_obs.copy_(self.obs)
+                self._g_dones.copy_(self.dones)
+                self._g_out = out[:7]
+            self.obs, self.dones = self._g_obs, self._g_dones
+        self._graph.replay()
+        return self._g_out + ([],)

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=131072)
 ap.add_argument("--nsteps", type=int, default=240)
 ap.add_argument("--rollouts", type=int, default=3)
+ap.add_argument("--eager", action="store_true", help="issue every launch from the host instead of replaying one CUDA graph per rollout")
 args = ap.parse_args()
 world, rank, lr = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr)
@@ -26,16 +27,17 @@ from gym_highway_b200.rollout import MlpPolicy, Runner
 torch.manual_seed(0)
 env = HighwayVecEnv(args.envs, seed=0, device=dev, env_id0=rank * args.envs)
 pol = MlpPolicy(18, 4, bf16_inference=True).to(dev)
-g = torch.Generator(device=dev); g.manual_seed(rank)
-run = Runner(env, pol, nsteps=args.nsteps, gamma=0.99, lam=0.95, generator=g)
-run.run(want_epinfos=False)  # warm-up rollout
+torch.cuda.manual_seed(rank)
+run = Runner(env, pol, nsteps=args.nsteps, gamma=0.99, lam=0.95, generator=None)
+collect = (lambda: run.run(want_epinfos=False)) if args.eager else run.run_graphed
+collect()  # warm-up rollout (and graph capture)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
 t0.record()
 for _ in range(args.rollouts):
-    out = run.run(want_epinfos=False)
+    out = collect()
     stats = env.episode_statistics(reset=True)  # one all_reduce of 8 counters per rollout
 t1.record()
 torch.cuda.synchronize()
@@ -45,7 +47,7 @@ if world > 1:
 if rank == 0:
     total = world * args.envs * args.nsteps * args.rollouts
     print(json.dumps({"workload": "ppo2 rollout collection, %d envs/GPU x %d GPU(s), T=%d, MLP 18-256-256-256 policy on device" % (args.envs, world, args.nsteps),
-                      "rollout_env_steps_per_s": total / (ms * 1e-3), "ms_per_rollout": ms / args.rollouts,
+                      "mode": "eager" if args.eager else "cuda graph", "rollout_env_steps_per_s": total / (ms * 1e-3), "ms_per_rollout": ms / args.rollouts,
                       "rollout_buffer_GB_per_gpu": args.nsteps * args.envs * 18 * 4 / 1e9, "last_rollout_episodes": stats}))
 if world > 1:
     dist.barrier(); dist.destroy_process_group()

@@ -34,6 +34,31 @@ def test_runner_collects_a_full_episode_on_device():
         assert torch.equal(ob, o[:, t + 1, :])
 
 
+def test_graphed_rollout_replays_real_transitions():
+    """the whole rollout replayed from one CUDA graph: the stored (obs, action, obs') triples are the env's own"""
+    from gym_highway_b200 import HighwayVecEnv
+    from gym_highway_b200.rollout import MlpPolicy, Runner
+    torch.manual_seed(0)
+    n, T = 1024, 16
+    pol = MlpPolicy(18, 4).cuda()
+    run = Runner(HighwayVecEnv(n, seed=1), pol, nsteps=T, generator=None)
+    out1 = [x.clone() for x in run.run_graphed()[:6]]        # warm-up rollout, capture, first replay
+    snapshot = {k: v.clone() for k, v in run.env.state_dict().items()}
+    start_obs = run.obs.clone()
+    obs, returns, masks, actions, values, neglogp = [x.clone() for x in run.run_graphed()[:6]]   # second replay
+    assert obs.shape == (n * T, 18) and torch.isfinite(returns).all() and actions.min() >= 0 and actions.max() <= 3
+    assert not torch.equal(out1[0], obs)
+    o, a = obs.reshape(n, T, 18), actions.reshape(n, T)
+    assert torch.equal(o[:, 0, :], start_obs)
+    ref = HighwayVecEnv(n, seed=1)
+    ref.load_state_dict(snapshot)
+    for t in range(T - 1):
+        ob, _, _, _ = ref.step(a[:, t].contiguous())
+        assert torch.equal(ob, o[:, t + 1, :]), t
+    with pytest.raises(ValueError):
+        Runner(HighwayVecEnv(8, seed=1), pol, nsteps=3, generator=None).run_graphed()
+
+
 def test_vec_monitor_on_the_real_env(tmp_path):
     from gym_highway_b200 import HighwayVecEnv
     from gym_highway_b200.monitor import VecMonitor, load_results
