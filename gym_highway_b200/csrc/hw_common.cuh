@@ -67,6 +67,27 @@ __device__ __forceinline__ void dmov_if_nz(uint32_t w, double &x, double y)
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmul.rn.f64 %0, %2, 0d3FF0000000000000;\nHW_SKIP:\n\t}" : "+d"(x) : "r"(w), "d"(y));
 }
 
+// a copy that costs ONE instruction (DMUL by 1.0) instead of the two 32-bit moves of a plain assignment; for values that
+// seed a chain of dmov_if's
+__device__ __forceinline__ double dcopy(double y)
+{
+    double r;
+    asm("mul.rn.f64 %0, %1, 0d3FF0000000000000;" : "=d"(r) : "d"(y));
+    return r;
+}
+
+// a, b or c for sel = 1, 2, anything else: three DMULs, the last two predicated
+__device__ __forceinline__ double dsel3(int sel, double a, double b, double c)
+{
+    double r;
+    asm("{\n\t.reg .pred p1, p2;\n\tsetp.eq.s32 p1, %4, 1;\n\tsetp.eq.s32 p2, %4, 2;\n\t"
+        "mul.rn.f64 %0, %3, 0d3FF0000000000000;\n\t"
+        "@!p2 bra HW_S2;\n\tmul.rn.f64 %0, %2, 0d3FF0000000000000;\nHW_S2:\n\t"
+        "@!p1 bra HW_S1;\n\tmul.rn.f64 %0, %1, 0d3FF0000000000000;\nHW_S1:\n\t}"
+        : "=&d"(r) : "d"(a), "d"(b), "d"(c), "r"(sel));
+    return r;
+}
+
 __device__ __forceinline__ void dset_if(bool p, double &x, double c)
 {
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmov.f64 %0, %2;\nHW_SKIP:\n\t}" : "+d"(x) : "r"((int)p), "d"(c));

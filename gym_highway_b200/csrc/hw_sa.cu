@@ -105,6 +105,7 @@ struct SaConsts {
     double k30dt;    // 30.0 * dt   (moveLeft / moveRight steering increment)
     int ticks_per_step;
     int timeout_tick;
+    double five_dt;  // 5.0 + dt: accelerate() on a clamped acceleration
 };
 
 // respawn (multi_lane_sim.py:963-991): opx < -2.375, pre-filtered on the hi words (negative doubles order reversed)
@@ -295,14 +296,12 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     // dlane = -1 / +1 / 0 for LEFT / RIGHT / the other actions is fixed for the step
     lane = (fire & (kBitLeft | kBitRight)) ? min(max(lane + dlane, 1), 3) : lane;
     const bool l1 = lane == 1, l2 = lane == 2, l3 = lane == 3;
-    double fpx = e.opx[2], fiv = e.oiv[2];
-    dmov_if(l2, fpx, e.opx[1]); dmov_if(l2, fiv, e.oiv[1]);
-    dmov_if(l1, fpx, e.opx[0]); dmov_if(l1, fiv, e.oiv[0]);
+    const double fpx = dsel3(lane, e.opx[0], e.opx[1], e.opx[2]), fiv = dsel3(lane, e.oiv[0], e.oiv[1], e.oiv[2]);
     {
         // maintain(): cruise = velocity of the vehicle ahead in the lane, else the car's own.  An obstacle that was held
         // back in the previous tick (e.slow) moved by fl(fl(x + vdt) - vdt) <= 10 from x < 10, so one that is ahead
         // (fpx > 10) moved with its own init_vx.
-        double cr = e.vx;
+        double cr = dcopy(e.vx);
         dmov_if(fpx > 10.0, cr, fiv);
         dmov_if_nz(fire & kBitDoMaint, e.cruise, cr);
     }
@@ -332,9 +331,8 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     const bool m_maint = (b & kBitDoMaint) != 0;  // never set together with do_accelerate
     {
         // accelerate(): acc = 0 if acc < 0 else acc + dt, on the acc the action stage clamped to <= 5
-        double acc_c = e.acc;
-        dset_if(5.0 < e.acc, acc_c, 5.0);
-        double acc_a = dadd(acc_c, dt);
+        double acc_a = dadd(e.acc, dt);
+        dmov_if(5.0 < e.acc, acc_a, K.five_dt);  // min(acc, 5) + dt
         dset_if(e.acc < 0.0, acc_a, 0.0);
         // maintain(): bang-bang towards ceil(cruise), snap when the ceilings agree
         const double vc = ceil(e.vx), cc = ceil(e.cruise);
@@ -354,16 +352,19 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     }
     const double vdt = dmul(e.vx, dt);
     e.rx = dadd(e.rx, vdt);
-    const bool m_left = (b & kBitLeft) != 0;
-    const bool m_right = (b & kBitRight) != 0;  // never set together with left_mode
-    if (m_left | m_right) {
+    if (b & (kBitLeft | kBitRight)) {  // the two never come together
         // steering clamp of the action stage (only a lane-change mode leaves steer != 0), then moveLeft/moveRight
-        double sc = e.steer, inc = K.k30dt;
+        double sc = e.steer;
         dmov_if(30.0 < fabs(e.steer), sc, copysign(30.0, e.steer));
-        dmov_if(m_right, inc, -K.k30dt);
+        // +30*dt in left mode, -30*dt in right mode: the right-mode bit (bit 19) moved onto the sign bit of the increment
+        const double inc = __hiloint2double(__double2hiint(K.k30dt) ^ (int)((b << 12) & 0x80000000u), __double2loint(K.k30dt));
         double st = dadd(sc, inc);
         const double ty = __hiloint2double(l1 ? 0x3FF40000 : (l2 ? 0x400E0000 : 0x40190000), 0);  // 1.25, 3.75, 6.25
-        const bool reached = (m_left && e.py <= ty) || (m_right && e.py >= ty);
+        int reached_i;  // (left_mode and y <= target) or (right_mode and y >= target): two compares and one predicate op
+        asm("{\n\t.reg .pred a, c, l, nl, r;\n\tsetp.ne.b32 l, %3, 0;\n\tnot.pred nl, l;\n\t"
+            "setp.le.and.f64 a, %1, %2, l;\n\tsetp.ge.and.f64 c, %1, %2, nl;\n\tor.pred r, a, c;\n\tselp.s32 %0, 1, 0, r;\n\t}"
+            : "=r"(reached_i) : "d"(e.py), "d"(ty), "r"(b & kBitLeft));
+        const bool reached = reached_i != 0;
         dset_if(reached, st, 0.0);
         if (reached) b &= ~(kBitLeft | kBitRight);
         e.steer = st;
@@ -645,6 +646,7 @@ static int launch_step_range(const HwSaState *st, const void *actions, const HwS
     SaConsts K;
     K.dt = P->dt;
     K.k30dt = 30.0 * P->dt;  // python: 30.0 * dt
+    K.five_dt = 5.0 + P->dt;
     K.ticks_per_step = P->ticks_per_step;
     K.timeout_tick = P->timeout_tick;
     const unsigned grid = (unsigned)((count + kSaBlock - 1) / kSaBlock);
