@@ -16,7 +16,10 @@
 
 namespace hw {
 
-constexpr int kSaBlock = 128;
+#ifndef HW_SA_BLOCK
+#define HW_SA_BLOCK 128
+#endif
+constexpr int kSaBlock = HW_SA_BLOCK;
 
 // Per-environment working set (registers).  ovx[] (each obstacle's velocity after its last update) is
 // only materialised at the step boundaries: inside a step it is init_vx, or the car's vx for the one
@@ -194,9 +197,20 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
     int ncol = 0;
     if (!lock) {
         constexpr uint32_t kLo = 0x401EA000u, kSpan = 0x4028C000u - 0x401EA000u;  // hi(7.65625), hi(12.375)
-        const bool near = (hi32(e.opx[0]) - kLo <= kSpan) || (hi32(e.opx[1]) - kLo <= kSpan) || (hi32(e.opx[2]) - kLo <= kSpan);
-        if (near || (FIRST && px != 10.0)) {
-            ncol = sa_collide_exact(px, e.py, e.opx[0], e.opx[1], e.opx[2]);
+        const bool n0 = hi32(e.opx[0]) - kLo <= kSpan, n1 = hi32(e.opx[1]) - kLo <= kSpan, n2 = hi32(e.opx[2]) - kLo <= kSpan;
+        if (FIRST) {
+            if (n0 || n1 || n2 || px != 10.0) {
+                ncol = sa_collide_exact(px, e.py, e.opx[0], e.opx[1], e.opx[2]);
+                ncoll_acc += ncol;
+            }
+        } else if (n0 | n1 | n2) {
+            // the car is pinned at x = 10: the x overlap is the interval itself, the y overlap of rect k (y = 21 + 80k,
+            // height 38) with the car's rect is |ay - by| <= 37 (see sa_tick_later)
+            const int ay = rect_y(e.py);
+            const bool c0 = n0 && e.opx[0] >= 7.65625 && e.opx[0] < 12.375 && (uint32_t)(ay - 21 + 37) <= 74u;
+            const bool c1 = n1 && e.opx[1] >= 7.65625 && e.opx[1] < 12.375 && (uint32_t)(ay - 101 + 37) <= 74u;
+            const bool c2 = n2 && e.opx[2] >= 7.65625 && e.opx[2] < 12.375 && (uint32_t)(ay - 181 + 37) <= 74u;
+            ncol = (c0 ? 1 : 0) + (c1 ? 1 : 0) + (c2 ? 1 : 0);
             ncoll_acc += ncol;
         }
     }
