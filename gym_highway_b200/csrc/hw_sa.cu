@@ -198,11 +198,10 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
     if (!lock) {
         constexpr uint32_t kLo = 0x401EA000u, kSpan = 0x4028C000u - 0x401EA000u;  // hi(7.65625), hi(12.375)
         const bool n0 = hi32(e.opx[0]) - kLo <= kSpan, n1 = hi32(e.opx[1]) - kLo <= kSpan, n2 = hi32(e.opx[2]) - kLo <= kSpan;
-        if (FIRST) {
-            if (n0 || n1 || n2 || px != 10.0) {
-                ncol = sa_collide_exact(px, e.py, e.opx[0], e.opx[1], e.opx[2]);
-                ncoll_acc += ncol;
-            }
+        if (FIRST && px != 10.0) {
+            // only a state the reference cannot produce (the car leaves x = 10 only at reset, under the collision lock)
+            ncol = sa_collide_exact(px, e.py, e.opx[0], e.opx[1], e.opx[2]);
+            ncoll_acc += ncol;
         } else if (n0 | n1 | n2) {
             // the car is pinned at x = 10: the x overlap is the interval itself, the y overlap of rect k (y = 21 + 80k,
             // height 38) with the car's rect is |ay - by| <= 37 (see sa_tick_later)

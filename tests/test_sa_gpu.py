@@ -112,6 +112,46 @@ def test_trajectory_parity_1000_steps(continuous, real_time):
     assert s["episodes"] == ndone
 
 
+@pytest.mark.parametrize("continuous", [False, True])
+def test_first_tick_handles_states_off_the_reference_manifold(continuous):
+    """States the reference cannot reach but a caller can inject: the car away from x = 10 on a running episode, obstacles
+    placed around it.  The first tick of a step is the generic one (exact rect test at the car's real x); the oracle is
+    generic throughout, so one step from such states must agree (the later ticks see the car pinned at 10 again)."""
+    n, seed = 8192, 11
+    rng = np.random.RandomState(3)
+    st = orc.SaState(n)
+    orc.sa_reset(st)
+    st.tick[:] = rng.randint(1, 2000, n)
+    st.car[:, 0] = f32(rng.uniform(4.0, 16.0, n))           # px
+    st.car[:, 1] = f32(rng.uniform(1.0, 6.9, n))            # py
+    st.car[:, 2] = f32(rng.uniform(20.0, 900.0, n))         # raw x
+    st.car[:, 3] = f32(rng.uniform(0.0, 20.0, n))           # vx
+    st.car[:, 4] = f32(rng.uniform(-5.0, 5.0, n))           # acc
+    st.lane[:] = rng.randint(1, 4, n)
+    if continuous:
+        st.car[:, 5] = f32(rng.uniform(-30.0, 30.0, n))
+    else:
+        st.flags[:] = rng.choice([0, 1, 2, 4, 8, 1 | 4, 2 | 8, 1 | 8, 2 | 4], n)
+        st.car[:, 5] = np.where(st.flags & 3, f32(rng.uniform(-30.0, 30.0, n)), 0.0)
+        st.car[:, 6] = f32(rng.uniform(0.0, 20.0, n))       # cruise
+    st.obst[:, :, 0] = f32(st.car[:, 0:1] + rng.uniform(-6.0, 30.0, (n, 3)))   # around the car: many rect overlaps
+    st.obst[:, :, 1] = f32(st.car[:, 2:3] + (st.obst[:, :, 0] - st.car[:, 0:1]))
+    st.obst[:, :, 3] = f32(rng.uniform(5.0, 7.0, (n, 3)))
+    st.obst[:, :, 2] = st.obst[:, :, 3]
+    env = _env(n, continuous=continuous, seed=seed, auto_reset=False, exact_steering=True)
+    _load_state(env, st)
+    act = rng.uniform(-1, 1, (n, 2)).astype(np.float32) if continuous else rng.randint(0, 4, n).astype(np.int32)
+    obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+    want = orc.sa_step(st, act, continuous=continuous, seed=seed, quantise=True, autoreset=False, nthreads=4)
+    assert int(want["done"].sum()) > n // 20                  # plenty of collisions in the sample
+    assert np.array_equal(done.cpu().numpy(), want["done"])
+    assert bits_equal(rew.cpu().numpy(), f32(want["rew"]))
+    assert bits_equal(obs.cpu().numpy(), want["obs"])
+    got = _read_state(env)
+    for f in got.FIELDS:
+        assert np.array_equal(getattr(got, f), getattr(st, f)), f
+
+
 def test_tail_block_and_small_batches():
     for n in (1, 2, 31, 127, 129, 1000):
         env = _env(n, seed=9, exact_steering=True)
