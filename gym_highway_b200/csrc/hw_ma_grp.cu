@@ -395,14 +395,15 @@ struct GrpStep {
         o2[0] = make_float2(norm_f64(c.acc, -5.0, 5.0), norm_f64(c.steer, -30.0, 30.0));
         o2[1] = make_float2(norm_f64(c.rx, 0.0, 1200.0), norm_f64(c.py, 0.0, 8.0));
         o2[2 + S] = make_float2(norm_f64(c.vx, -20.0, 20.0), norm_f64(c.vy, -20.0, 20.0));
-        // other cars: slot j - (j > a)
+        // other cars: car j goes to slot j - (j > a).  Walked by slot (j = s + (s >= a)) so that the lanes of a warp stay
+        // converged: skipping "j == own index" inside a loop over j makes every lane skip a different iteration
 #pragma unroll
-        for (int j = 0; j < kMaxA; ++j) {
-            if (AT ? (j >= AT) : false) break;
-            if (j >= A || j == g) continue;
-            const int s = j - (j > g ? 1 : 0);
-            o2[2 + s] = make_float2(norm_f64(dsub(pc[P_RX * CS + j], c.rx), -60.0, 60.0), norm_f64(dsub(pc[P_PY * CS + j], c.py), -8.0, 8.0));
-            o2[3 + S + s] = make_float2(norm_f64(dsub(pc[(P_VX0 + cur) * CS + j], c.vx), -20.0, 20.0), norm_f64(dsub(pc[P_VY * CS + j], c.vy), -20.0, 20.0));
+        for (int sl = 0; sl < kMaxA - 1; ++sl) {
+            if (AT ? (sl >= AT - 1) : false) break;
+            if (sl >= A - 1) break;
+            const int j = sl + (sl >= g ? 1 : 0);
+            o2[2 + sl] = make_float2(norm_f64(dsub(pc[P_RX * CS + j], c.rx), -60.0, 60.0), norm_f64(dsub(pc[P_PY * CS + j], c.py), -8.0, 8.0));
+            o2[3 + S + sl] = make_float2(norm_f64(dsub(pc[(P_VX0 + cur) * CS + j], c.vx), -20.0, 20.0), norm_f64(dsub(pc[P_VY * CS + j], c.vy), -20.0, 20.0));
         }
         // per lane the obstacle nearest in raw x (first wins ties, insertion order): slot A-1+lane
         double nd0 = dinf(), nd1 = dinf(), nd2 = dinf();
