@@ -111,6 +111,30 @@ def test_policy_shapes_on_cpu():
     assert sum(p.numel() for p in pol.body.parameters()) == 18 * 256 + 256 + 2 * (256 * 256 + 256)
 
 
+def test_policy_bf16_inference_path_and_sampler():
+    """rollout-time forward (bf16 weights, fused bias+ReLU GEMMs, padded widths) tracks the fp32 modules, is refreshed when
+    the parameters change, and the inverse-CDF sampler follows the categorical distribution"""
+    from gym_highway_b200.rollout import MlpPolicy
+    torch.manual_seed(0)
+    pol = MlpPolicy(18, 4)
+    x = torch.rand(2048, 18)
+    with torch.no_grad():
+        logits, v = pol.forward(x)
+        l16, v16 = pol._forward_bf16(x)
+        assert l16.shape == logits.shape and v16.shape == v.shape
+        assert (l16 - logits).abs().max() < 5e-3 and (v16 - v).abs().max() < 5e-3
+        pol.pi.bias.add_(1.0)                      # in-place update, as an optimiser step would do
+        l16b, _ = pol._forward_bf16(x)
+        assert ((l16b - l16) - 1.0).abs().max() < 2e-2
+        # sampler: empirical frequencies of one fixed distribution
+        pol.pi.weight.zero_(); pol.pi.bias.copy_(torch.log(torch.tensor([0.1, 0.2, 0.3, 0.4])))
+        a, val, nlp = pol.step(torch.rand(200000, 18))
+        assert a.dtype == torch.int32 and a.min() >= 0 and a.max() <= 3
+        freq = torch.bincount(a.long(), minlength=4).double() / a.numel()
+        assert (freq - torch.tensor([0.1, 0.2, 0.3, 0.4], dtype=torch.float64)).abs().max() < 5e-3
+        assert torch.allclose(nlp, -torch.log(torch.tensor([0.1, 0.2, 0.3, 0.4]))[a.long()], atol=1e-5)
+
+
 def test_spaces_and_bounds():
     low, high = highway_obs_bounds(4, np.float32)
     assert low.shape == (18,) and low.dtype == np.float32
