@@ -205,3 +205,41 @@ class Runner(object):
             self.obs, self.dones = self._g_obs, self._g_dones
         self._graph.replay()
         return self._g_out + ([],)
+
+
+class A2CRunner(object):
+    """a2c's Runner over a GPU VecEnv (baselines/a2c/runner.py:21-72): `run()` returns
+    (obs, states, rewards, masks, actions, values) flattened environment-major, where `rewards` are the n-step discounted
+    returns bootstrapped off the value function where the last step did not end the episode, and `masks[e, t]` says whether
+    the episode of env e ended on the transition BEFORE step t."""
+
+    def __init__(self, env, model, nsteps=5, gamma=0.99, generator=None):
+        self.env, self.model, self.nsteps, self.gamma, self.generator = env, model, nsteps, gamma, generator
+        self.obs = env.reset().clone()
+        n, dev = env.num_envs, self.obs.device
+        cont = getattr(env, "continuous", False)
+        self.dones = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.mb_obs = torch.empty((nsteps, n) + tuple(self.obs.shape[1:]), dtype=torch.float32, device=dev)
+        self.mb_rewards = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
+        self.mb_actions = torch.empty((nsteps, n, 2) if cont else (nsteps, n), dtype=torch.float32 if cont else torch.int32, device=dev)
+        self.mb_values = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
+        self.mb_dones = torch.empty(nsteps + 1, n, dtype=torch.float32, device=dev)
+
+    @torch.no_grad()
+    def run(self):
+        for t in range(self.nsteps):
+            actions, values, _ = self.model.step(self.obs, generator=self.generator)
+            self.mb_obs[t].copy_(self.obs)
+            self.mb_actions[t].copy_(actions)
+            self.mb_values[t].copy_(values)
+            self.mb_dones[t].copy_(self.dones)
+            obs, rewards, dones, _ = self.env.step(actions)
+            self.obs = obs
+            self.dones = dones.to(torch.float32)
+            self.mb_rewards[t].copy_(rewards)
+        self.mb_dones[self.nsteps].copy_(self.dones)
+        masks, dones = self.mb_dones[:-1], self.mb_dones[1:]
+        rewards = self.mb_rewards
+        if self.gamma > 0.0:
+            rewards = discount_with_dones(self.mb_rewards, dones, self.gamma, bootstrap=self.model.value(self.obs))
+        return sf01(self.mb_obs), None, sf01(rewards), sf01(masks), sf01(self.mb_actions), sf01(self.mb_values)

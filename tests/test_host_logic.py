@@ -101,6 +101,61 @@ def test_gae_sf01_and_nstep_returns_match_the_runner_formulas():
         assert np.allclose(out[:, n], want, atol=1e-5)
 
 
+def test_a2c_runner_matches_the_reference_loop_on_a_toy_env():
+    """A2CRunner against a literal transcription of baselines/a2c/runner.py:21-72 + a2c/utils.py discount_with_dones,
+    over a deterministic toy VecEnv (the runner only needs reset/step/num_envs)"""
+    class ToyEnv(object):
+        num_envs, continuous = 6, False
+        def __init__(self):
+            self.t = 0
+        def reset(self):
+            self.t = 0
+            return torch.zeros(self.num_envs, 18)
+        def step(self, actions):
+            self.t += 1
+            g = torch.Generator().manual_seed(self.t)
+            obs = torch.rand(self.num_envs, 18, generator=g)
+            rew = torch.rand(self.num_envs, generator=g) - 0.5
+            done = torch.rand(self.num_envs, generator=g) < 0.3
+            return obs, rew, done, None
+    torch.manual_seed(1)
+    pol = rollout.MlpPolicy(18, 4)
+    T, gamma = 7, 0.9
+    run = rollout.A2CRunner(ToyEnv(), pol, nsteps=T, gamma=gamma, generator=torch.Generator().manual_seed(3))
+    for _ in range(2):   # second rollout starts mid-episode with carried dones
+        obs0, dones0 = run.obs.clone(), run.dones.clone()
+        env_t0 = run.env.t
+        gstate = run.generator.get_state()
+        obs, states, rewards, masks, actions, values = run.run()
+        # reference loop
+        ref_env = ToyEnv(); ref_env.t = env_t0
+        g = torch.Generator(); g.set_state(gstate)
+        o, d = obs0, dones0
+        mb_r, mb_d, mb_v = [], [], []
+        with torch.no_grad():
+            for n in range(T):
+                a, v, _ = pol.step(o, generator=g)
+                mb_d.append(d.clone()); mb_v.append(v)
+                o, r, dn, _ = ref_env.step(a)
+                d = dn.float(); mb_r.append(r)
+            mb_d.append(d.clone())
+            last = pol.value(o).tolist()
+        R = torch.stack(mb_r).t().tolist(); D = torch.stack(mb_d).t()
+        m_ref, d_ref = D[:, :-1], D[:, 1:].tolist()
+        def dwd(rewards, dones, gamma):
+            out, r = [], 0.0
+            for rew, dn in zip(rewards[::-1], dones[::-1]):
+                r = rew + gamma * r * (1.0 - dn); out.append(r)
+            return out[::-1]
+        want = []
+        for rews, dns, val in zip(R, d_ref, last):
+            want.append(dwd(rews + [val], dns + [0], gamma)[:-1] if dns[-1] == 0 else dwd(rews, dns, gamma))
+        assert states is None and obs.shape == (6 * T, 18) and actions.shape == (6 * T,)
+        assert torch.allclose(rewards.reshape(6, T), torch.tensor(want), atol=1e-5)
+        assert torch.equal(masks.reshape(6, T), m_ref)
+        assert torch.allclose(values.reshape(6, T), torch.stack(mb_v).t(), atol=1e-6)
+
+
 def test_policy_shapes_on_cpu():
     pol = rollout.MlpPolicy(18, 4)
     a, v, nl = pol.step(torch.rand(5, 18))
