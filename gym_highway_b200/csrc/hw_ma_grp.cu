@@ -31,25 +31,26 @@ template <int G>
 struct GrpLayout {
     static constexpr int kEnvsPerWarp = 32 / G;
     static constexpr int kEnvs = kEnvsPerWarp * kGrpWarps;  // environments per block
-    // published car fields (doubles): px, py, rx, vy, vx[2] (double buffered); ints: lane (old << 8 | new), rect x, rect y
+    // published car fields (doubles): px, py, rx, vy, vx[2] (double buffered); ints: lane (old << 8 | new), rect {x, y}
     static constexpr int kCarD = 6, kCarI = 3;
     // obstacle slots of one environment are contiguous (slot k of field f at ob[f][e * kObStride + k]): the loops that
     // walk the list index with one add; the odd stride keeps the groups of a warp on different banks
     static constexpr int kObStride = kMaxK + 1;
     static constexpr size_t kDoubles = (size_t)(kCarD + 1) * kEnvs * G + (size_t)O_NF * kEnvs * kObStride;
-    static constexpr size_t kInts = (size_t)kCarI * kEnvs * G + (size_t)kEnvs * kObStride;
+    static constexpr size_t kInts = (size_t)kCarI * kEnvs * G + (size_t)2 * kEnvs * kObStride;  // + one rect {x, y} per obstacle slot
     static constexpr size_t kBytes = kDoubles * sizeof(double) + kInts * sizeof(int);
 };
 
 enum { P_PX = 0, P_PY, P_RX, P_VY, P_VX0, P_VX1 };
-enum { I_LANE = 0, I_RECTX, I_RECTY };
+enum { I_LANE = 0, I_RECT };  // I_RECT: int2 per car, two ints wide
 
 template <int G>
 struct GrpSm {
     using L = GrpLayout<G>;
     static constexpr int OS = L::kEnvs * L::kObStride;  // stride between obstacle fields
     double *car, *ob, *rew;
-    int *ci, *obx;
+    int *ci;
+    int2 *obr;  // rect {x, y} per obstacle slot ({0, 0} = pygame's default rect of a slot spawned in this tick)
     int e;  // environment within the block
     __device__ __forceinline__ GrpSm(double *base, int e_) : e(e_)
     {
@@ -57,15 +58,16 @@ struct GrpSm {
         double *ob0 = car + (size_t)L::kCarD * L::kEnvs * G;
         rew = ob0 + (size_t)O_NF * OS;
         ci = reinterpret_cast<int *>(rew + (size_t)L::kEnvs * G);
-        int *obx0 = ci + (size_t)L::kCarI * L::kEnvs * G;
+        int2 *obr0 = reinterpret_cast<int2 *>(ci + (size_t)L::kCarI * L::kEnvs * G);
         ob = ob0 + e * L::kObStride;
-        obx = obx0 + e * L::kObStride;
+        obr = obr0 + e * L::kObStride;
     }
     __device__ __forceinline__ double &c(int f, int a) const { return car[((size_t)f * L::kEnvs + e) * G + a]; }
     __device__ __forceinline__ int &i(int f, int a) const { return ci[((size_t)f * L::kEnvs + e) * G + a]; }
     __device__ __forceinline__ double &r(int a) const { return rew[(size_t)e * G + a]; }
     __device__ __forceinline__ double &o(int f, int k) const { return ob[f * OS + k]; }
-    __device__ __forceinline__ int &ox(int k) const { return obx[k]; }
+    __device__ __forceinline__ int2 &orect(int k) const { return obr[k]; }
+    __device__ __forceinline__ int2 &crect(int a) const { return reinterpret_cast<int2 *>(ci + (size_t)I_RECT * L::kEnvs * G)[(size_t)e * G + a]; }
 };
 
 struct GrpCar {  // the lane's own car, registers
@@ -89,6 +91,7 @@ __device__ __forceinline__ void grp_reset_env(MaHead &h, GrpCar &c, const GrpSm<
     if (g < 3) {
         const double ox = (g == 0) ? -20.0 : (g == 1) ? -25.0 : -40.0, ov = (g == 0) ? 7.0 : (g == 1) ? 5.0 : 6.0;
         sm.o(O_PX, g) = ox; sm.o(O_RX, g) = ox; sm.o(O_VX, g) = ov; sm.o(O_IV, g) = ov;
+        sm.orect(g) = make_int2(0, 0);  // not yet updated: pygame's default rect
     }
     h.nobs = 3; h.olane = 1u | (2u << 2) | (3u << 4); h.ofresh = 7u;
     h.newest[0] = 0; h.newest[1] = 1; h.newest[2] = 2;
@@ -101,7 +104,7 @@ __device__ __forceinline__ void grp_publish(const GrpCar &c, const GrpSm<G> &sm,
 {
     sm.c(P_PX, g) = c.px; sm.c(P_PY, g) = c.py; sm.c(P_RX, g) = c.rx; sm.c(P_VY, g) = c.vy; sm.c(P_VX0 + cur, g) = c.vx;
     sm.i(I_LANE, g) = car_lane(c.b);
-    sm.i(I_RECTX, g) = rect_x(c.px); sm.i(I_RECTY, g) = rect_y(c.py);
+    sm.crect(g) = make_int2(rect_x(c.px), rect_y(c.py));
 }
 
 __device__ __forceinline__ double dinf() { return __longlong_as_double(0x7FF0000000000000ll); }
@@ -279,7 +282,7 @@ struct GrpStep {
             const double odt = dmul(v, dt);
             const double opx = dsub(dadd(sm.o(O_PX, k), odt), lvdt);
             sm.o(O_VX, k) = v; sm.o(O_PX, k) = opx; sm.o(O_RX, k) = dadd(orx, odt);
-            sm.ox(k) = rect_x(opx);
+            sm.orect(k) = make_int2(rect_x(opx), 80 * lane - 59);  // y = 21 + 80 * (lane - 1)
         }
         h.ofresh = 0;  // every live obstacle has now written its rect
         lead = 0; last = 0;
@@ -328,6 +331,7 @@ struct GrpStep {
                     const int nk = (int)h.nobs;
                     sm.o(O_PX, nk) = x; sm.o(O_RX, nk) = dadd(pc[P_RX * CS + lead], dsub(x, pc[P_PX * CS + lead]));
                     sm.o(O_VX, nk) = v; sm.o(O_IV, nk) = v;
+                    sm.orect(nk) = make_int2(0, 0);
                     h.olane = (h.olane & ~(3u << (2 * nk))) | ((uint32_t)(lane + 1) << (2 * nk));
                     h.ofresh |= 1u << nk;
                     h.newest[lane] = (uint32_t)nk;
@@ -344,7 +348,7 @@ struct GrpStep {
             if (dsub(sm.o(O_RX, k), last_rx) < thr) continue;
             if (w != k) {
                 sm.o(O_PX, w) = sm.o(O_PX, k); sm.o(O_RX, w) = sm.o(O_RX, k); sm.o(O_VX, w) = sm.o(O_VX, k); sm.o(O_IV, w) = sm.o(O_IV, k);
-                sm.ox(w) = sm.ox(k);
+                sm.orect(w) = sm.orect(k);
             }
             nl |= (uint32_t)ob_lane(h, k) << (2 * w);
             nf |= ((h.ofresh >> k) & 1u) << w;
@@ -366,18 +370,19 @@ struct GrpStep {
     // ---- Scenario.rewards -> check_collisions, after the updates and spawns of this tick (highway_core.py:401-422) ----
     __device__ __forceinline__ bool collide()
     {
-        const int ax = pi[I_RECTX * CS + g], ay = pi[I_RECTY * CS + g];
+        // rects are 76 x 38: A overlaps B iff |ax - bx| < 76 and |ay - by| < 38, each as one unsigned compare
+        const int2 ar = sm.crect(g);
+        const int ax75 = ar.x + 75, ay37 = ar.y + 37;
         int no = 0, na = 0;
         for (int k = 0; k < (int)h.nobs; ++k) {
-            const bool fresh = (h.ofresh >> k) & 1u;  // spawned in this tick: still pygame's default rect (0, 0, 76, 38)
-            const int bx = fresh ? 0 : sm.ox(k);
-            const int by = fresh ? 0 : (80 * ob_lane(h, k) - 59);  // 21 + 80 * (lane - 1)
-            no += rects_overlap(ax, ay, bx, by) ? 1 : 0;
+            const int2 br = sm.orect(k);
+            no += ((uint32_t)(ax75 - br.x) <= 150u) & ((uint32_t)(ay37 - br.y) <= 74u);
         }
 #pragma unroll
         for (int j = 0; j < kMaxA; ++j) {
             if (AT ? (j >= AT) : false) break;
-            na += ((j < A) & (j != g) & rects_overlap(ax, ay, pi[I_RECTX * CS + j], pi[I_RECTY * CS + j])) ? 1 : 0;
+            const int2 br = sm.crect(j);
+            na += (j < A) & (j != g) & ((uint32_t)(ax75 - br.x) <= 150u) & ((uint32_t)(ay37 - br.y) <= 74u);
         }
         const bool is_car = g < A;
         no = is_car ? no : 0; na = is_car ? na : 0;
@@ -445,7 +450,7 @@ struct GrpStep {
         for (int k = g; k < (int)h.nobs; k += G) {
             const float4 o = S.obst[(int64_t)k * n + i];
             sm.o(O_PX, k) = o.x; sm.o(O_RX, k) = o.y; sm.o(O_VX, k) = o.z; sm.o(O_IV, k) = o.w;
-            sm.ox(k) = rect_x((double)o.x);
+            sm.orect(k) = ((h.ofresh >> k) & 1u) ? make_int2(0, 0) : make_int2(rect_x((double)o.x), 80 * ob_lane(h, k) - 59);
         }
         cur = 0;
         grp_publish<G>(c, sm, g, cur);
@@ -549,13 +554,14 @@ ma_grp_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
     }
 
     // rewards of the step: summed in id order for shared_reward (highway_env.py:92-94) and for Monitor; collision counters
-    if (live) { st.sm.r(g) = st.reward; st.pi[I_RECTX * st.CS + g] = st.no_acc; st.pi[I_RECTY * st.CS + g] = st.na_acc; }
+    if (live) { st.sm.r(g) = st.reward; st.sm.crect(g) = make_int2(st.no_acc, st.na_acc); }  // the rect slot is free now
     __syncwarp();
     if (live) {
         double r = st.reward, rsum = 0.0;
         for (int a = 0; a < A; ++a) {
             rsum = dadd(rsum, st.sm.r(a));
-            st.h.nc_obs += (uint32_t)st.pi[I_RECTX * st.CS + a]; st.h.nc_agent += (uint32_t)st.pi[I_RECTY * st.CS + a];
+            const int2 cnt = st.sm.crect(a);
+            st.h.nc_obs += (uint32_t)cnt.x; st.h.nc_agent += (uint32_t)cnt.y;
         }
         if (shared_reward) {
             r = rsum;
