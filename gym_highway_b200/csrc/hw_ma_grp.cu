@@ -258,12 +258,30 @@ struct GrpStep {
         cur = nxt;
     }
 
-    // ---- obstacle updates (agent.py:223-260): yield to the nearest car ahead in the lane, by raw x; then the
-    //      leader / last election: stable sort by x, descending (highway_core.py:294-297) ----
-    __device__ __forceinline__ void obstacles_and_leader(const MaConsts &C)
+    // ---- leader / last election: stable sort of the cars by x, descending (highway_core.py:294-297), then the obstacle
+    //      updates (agent.py:223-260): yield to the nearest car ahead in the lane, by raw x.  In the reference the
+    //      election follows the obstacle updates, but it only reads the cars, which are final by now; doing it first
+    //      lets the lane that updates a slot also test it for a spawn (highway_core.py:300-323: the lane's newest
+    //      obstacle has fallen behind x = -2.375) or a retire (:327-342), both rare, while the values are in registers.
+    //      Returns whether this lane saw either condition.
+    __device__ __forceinline__ bool obstacles_and_leader(const MaConsts &C, const bool inf_obs, double &thr, double &last_rx)
     {
         const double dt = C.dt;
-        const double lvdt = dmul(pc[(P_VX0 + cur) * CS + (int)h.leader], dt);
+        const double lvdt = dmul(pc[(P_VX0 + cur) * CS + (int)h.leader], dt);  // last tick's leader, this tick's velocity
+        lead = 0; last = 0;
+        double plead = pc[P_PX * CS], plast = plead;
+#pragma unroll
+        for (int j = 1; j < kMaxA; ++j) {
+            if (AT ? (j >= AT) : false) break;
+            const double p = pc[P_PX * CS + j];
+            const bool up = (j < A) & (p > plead), dn = (j < A) & (p <= plast);  // first of the maxima, last of the minima
+            lead = up ? j : lead; dmov_if(up, plead, p);
+            last = dn ? j : last; dmov_if(dn, plast, p);
+        }
+        h.leader = (uint32_t)lead;
+        thr = dsub(dsub(-2.375, plead), 2.0);
+        last_rx = pc[P_RX * CS + last];
+        bool want = false;
         for (int k = g; k < (int)h.nobs; k += G) {
             const int lane = ob_lane(h, k);
             const double orx = sm.o(O_RX, k), iv = sm.o(O_IV, k);
@@ -281,36 +299,14 @@ struct GrpStep {
             dmov_if(bv < iv, v, bv);
             const double odt = dmul(v, dt);
             const double opx = dsub(dadd(sm.o(O_PX, k), odt), lvdt);
-            sm.o(O_VX, k) = v; sm.o(O_PX, k) = opx; sm.o(O_RX, k) = dadd(orx, odt);
+            const double orx2 = dadd(orx, odt);
+            sm.o(O_VX, k) = v; sm.o(O_PX, k) = opx; sm.o(O_RX, k) = orx2;
             sm.orect(k) = make_int2(rect_x(opx), 80 * lane - 59);  // y = 21 + 80 * (lane - 1)
+            const uint32_t newest = (lane == 1) ? h.newest[0] : (lane == 2) ? h.newest[1] : h.newest[2];
+            want = want | ((newest == (uint32_t)k) & (opx < -2.375)) | (dsub(orx2, last_rx) < thr);
         }
         h.ofresh = 0;  // every live obstacle has now written its rect
-        lead = 0; last = 0;
-        double plead = pc[P_PX * CS], plast = plead;
-#pragma unroll
-        for (int j = 1; j < kMaxA; ++j) {
-            if (AT ? (j >= AT) : false) break;
-            const double p = pc[P_PX * CS + j];
-            const bool up = (j < A) & (p > plead), dn = (j < A) & (p <= plast);  // first of the maxima, last of the minima
-            lead = up ? j : lead; dmov_if(up, plead, p);
-            last = dn ? j : last; dmov_if(dn, plast, p);
-        }
-        h.leader = (uint32_t)lead;
-    }
-
-    // ---- spawn (highway_core.py:300-323) and retire (:327-342) are rare: every lane looks for the conditions ... ----
-    __device__ __forceinline__ bool spawn_retire_wanted(double &thr, double &last_rx) const
-    {
-        bool want = false;
-#pragma unroll
-        for (int lane = 0; lane < 3; ++lane) {
-            const uint32_t s = h.newest[lane];
-            want = want | ((s < 31u) & (sm.o(O_PX, (int)(s & 15u)) < -2.375));
-        }
-        thr = dsub(dsub(-2.375, pc[P_PX * CS + lead]), 2.0);
-        last_rx = pc[P_RX * CS + last];
-        for (int k = g; k < (int)h.nobs; k += G) want = want | (dsub(sm.o(O_RX, k), last_rx) < thr);
-        return want;
+        return inf_obs && want;
     }
 
     // ... and lane 0 of the group does the serial slot bookkeeping
@@ -529,11 +525,10 @@ ma_grp_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
         __syncwarp();
         if (st.active) st.update_position(C);
         __syncwarp();
-        if (st.active) st.obstacles_and_leader(C);
+        double thr = 0.0, last_rx = 0.0;
+        const bool want = st.active && st.obstacles_and_leader(C, inf_obs, thr, last_rx);
         __syncwarp();
         if (inf_obs) {
-            double thr = 0.0, last_rx = 0.0;
-            const bool want = st.active && st.spawn_retire_wanted(thr, last_rx);
             const unsigned wanted = __ballot_sync(FULL, want);
             if (wanted) {  // some group of the warp has an obstacle to spawn or to retire
                 const bool mine = st.group_bits(wanted) != 0u;
