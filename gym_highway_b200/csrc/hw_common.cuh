@@ -32,24 +32,6 @@ __device__ __forceinline__ double ddiv_const(double x, const double c)
     return __fma_rn(__fma_rn(-q0, c, x), rc, q0);
 }
 
-// The max is spelled in PTX: NVVM turns the C++ ternary into max.f64, whose NaN-aware expansion on sm_100a is
-// six instructions (DSETP.MAX, two moves, SEL, FSEL, a predicated LOP3) instead of a compare and two selects.
-__device__ __forceinline__ double py_max(double lo, double x)  // x if x > lo else lo
-{
-    double r;
-    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(x), "d"(lo));
-    return r;
-}
-
-// p ? a : b as selp.f64 (two 32-bit selects); spelled in PTX where NVVM would otherwise turn a chain of
-// selects into divergent branches
-__device__ __forceinline__ double dsel(bool p, double a, double b)
-{
-    double r;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\tselp.f64 %0, %1, %2, q;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
-    return r;
-}
-
 // Conditional moves of doubles, spelled in PTX as a branch around one instruction so that ptxas predicates that
 // instruction instead of emitting the FSEL pair a C++ ternary gives.  Why: the step kernels are bound by
 // instruction issue, and within that by the 16-lane ALU pipe that executes FSEL / ISETP / LOP3 (it was ~70 % busy
@@ -93,7 +75,9 @@ __device__ __forceinline__ void dset_if(bool p, double &x, double c)
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmov.f64 %0, %2;\nHW_SKIP:\n\t}" : "+d"(x) : "r"((int)p), "d"(c));
 }
 
-// python max(lo, min(x, hi)): min keeps x unless hi < x; max keeps lo unless the inner value is > lo
+// python max(lo, min(x, hi)): min keeps x unless hi < x; max keeps lo unless the inner value is > lo.  (Spelled with
+// conditional moves: NVVM turns the C++ ternary `(x > lo) ? x : lo` into max.f64, whose NaN-aware expansion on sm_100a is
+// six instructions.)
 __device__ __forceinline__ double py_clamp(double x, const double lo, const double hi)
 {
     dset_if(hi < x, x, hi);
