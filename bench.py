@@ -324,6 +324,9 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": info["dtype"], "data": "synthetic",
             "config": {"workload": info["name"], "envs_per_gpu": n, "ticks_per_step": 9,
+                       "baseline_config": ("BASELINE.json configs[4] (scaling sweep 4k-16M envs, HBM GB/s vs roofline): the %d-env point, weak-scaled over the GPUs; "
+                                           "configs[1] (65,536 envs on one GPU, launch/latency-bound) is measured in the same run and reported under \"configs1\"" % n)
+                                          if info["kind"] == "sa" else "BASELINE.json configs[2]/[4]: multi-agent env, %d-env point" % n,
                        "l2": "flushed between timed launches (256 MiB overwrite outside the event pairs)" if flush
                              else "inputs larger than L2 (%.0f MB per launch vs 126 MB), no flush" % (working_set / 1e6),
                        "parallelism": "independent env shards, %d rank(s), no data-path collective" % world},
