@@ -520,6 +520,7 @@ ma_grp_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
         if (!CONT) {
             __syncwarp();
             if (st.active && (st.fire & kBitDoMaint)) st.maintain_search();
+            __syncwarp();  // the searches read the packed old / new lanes, which update_velocity overwrites
         }
         if (st.active) st.update_velocity(C);
         __syncwarp();
