@@ -187,9 +187,14 @@ struct GrpStep {
             const bool take = (j < A) & (j != g) & (lj == lane) & (opx > c.px) & (opx < bpx);
             dmov_if(take, bpx, opx); dmov_if(take, bvx, ovx);
         }
-        for (int k = 0; k < (int)h.nobs; ++k) {
+        // only the slots that drive in this lane (usually one): 2-bit lane fields of `olane` equal to `lane`, in slot order
+        const uint32_t diff = h.olane ^ ((uint32_t)lane * 0x55555555u);
+        uint32_t same = ~(diff | (diff >> 1)) & 0x55555555u & ((1u << (2 * h.nobs)) - 1u);
+        while (same) {
+            const int k = (__ffs((int)same) - 1) >> 1;
+            same &= same - 1u;
             const double opx = sm.o(O_PX, k), ovx = sm.o(O_VX, k);
-            const bool take = (ob_lane(h, k) == lane) & (opx > c.px) & (opx < bpx);
+            const bool take = (opx > c.px) & (opx < bpx);
             dmov_if(take, bpx, opx); dmov_if(take, bvx, ovx);
         }
         c.cruise = bvx;
@@ -406,23 +411,23 @@ struct GrpStep {
             o2[2 + sl] = make_float2(norm_f64(dsub(pc[P_RX * CS + j], c.rx), -60.0, 60.0), norm_f64(dsub(pc[P_PY * CS + j], c.py), -8.0, 8.0));
             o2[3 + S + sl] = make_float2(norm_f64(dsub(pc[(P_VX0 + cur) * CS + j], c.vx), -20.0, 20.0), norm_f64(dsub(pc[P_VY * CS + j], c.vy), -20.0, 20.0));
         }
-        // per lane the obstacle nearest in raw x (first wins ties, insertion order): slot A-1+lane
-        double nd0 = dinf(), nd1 = dinf(), nd2 = dinf();
-        double rx0 = 0.0, rx1 = 0.0, rx2 = 0.0, vx0 = 0.0, vx1 = 0.0, vx2 = 0.0;
-        for (int k = 0; k < (int)h.nobs; ++k) {
-            const int l = ob_lane(h, k);
-            const double orx = sm.o(O_RX, k), ovx = sm.o(O_VX, k);
-            const double d = fabs(dsub(c.rx, orx));
-            const bool t0 = (l == 1) & (d < nd0), t1 = (l == 2) & (d < nd1), t2 = (l == 3) & (d < nd2);
-            dmov_if(t0, nd0, d); dmov_if(t0, rx0, orx); dmov_if(t0, vx0, ovx);
-            dmov_if(t1, nd1, d); dmov_if(t1, rx1, orx); dmov_if(t1, vx1, ovx);
-            dmov_if(t2, nd2, d); dmov_if(t2, rx2, orx); dmov_if(t2, vx2, ovx);
-        }
+        // per lane the obstacle nearest in raw x (first wins ties, insertion order): slot A-1+lane.  The slots of a lane are
+        // picked out of the 2-bit lane fields of `olane`, so each slot is visited once, by its own lane's search.
+        const uint32_t live = (1u << (2 * h.nobs)) - 1u;
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             const int s = A - 1 + l;
-            const double nd = (l == 0) ? nd0 : (l == 1) ? nd1 : nd2;
-            const double orx = (l == 0) ? rx0 : (l == 1) ? rx1 : rx2, ovx = (l == 0) ? vx0 : (l == 1) ? vx1 : vx2;
+            const uint32_t diff = h.olane ^ ((uint32_t)(l + 1) * 0x55555555u);
+            uint32_t same = ~(diff | (diff >> 1)) & 0x55555555u & live;
+            double nd = dinf(), orx = 0.0, ovx = 0.0;
+            while (same) {
+                const int k = (__ffs((int)same) - 1) >> 1;
+                same &= same - 1u;
+                const double krx = sm.o(O_RX, k), kvx = sm.o(O_VX, k);
+                const double d = fabs(dsub(c.rx, krx));
+                const bool take = d < nd;
+                dmov_if(take, nd, d); dmov_if(take, orx, krx); dmov_if(take, ovx, kvx);
+            }
             float2 pos = make_float2(norm_f64(dsub(orx, c.rx), -60.0, 60.0), norm_f64(dsub(lane_centre(l), c.py), -8.0, 8.0));
             float2 vel = make_float2(norm_f64(dsub(ovx, c.vx), -20.0, 20.0), norm_f64(dsub(0.0, c.vy), -20.0, 20.0));
             if (!(nd < dinf())) {  // the reference raises here; flag it and emit the centre of the range
