@@ -4,8 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gym_highway_b200 import HighwayVecEnv
 
-def probe(n, cont=False, steps=60):
-    env = HighwayVecEnv(n, continuous=cont, seed=0)
+def probe(n, cont=False, steps=60, exact=bool(int(os.environ.get('HW_EXACT', '0')))):
+    env = HighwayVecEnv(n, continuous=cont, seed=0, exact_steering=exact)
     env.rollout_random(150)
     g = torch.Generator(device='cuda'); g.manual_seed(1)
     acts = (torch.rand((8, n, 2), generator=g, device='cuda') * 2 - 1) if cont else torch.randint(0, 4, (8, n), generator=g, device='cuda', dtype=torch.int32)
