@@ -1,4 +1,4 @@
-// Multi-agent highway step for sm_100a, G lanes per environment (G = 8: four environments per warp).
+// Multi-agent highway step for sm_100a, G lanes per environment (G = 5: six environments per warp, two idle lanes).
 //
 // Same path as hw_ma.cu (thread per environment): MultiAgentEnv.step, highway_core.HighwaySimulator.act,
 // agent.Car.update_d/update_c, agent.Obstacle.update, check_collisions, Scenario.rewards/observations, the
@@ -9,7 +9,8 @@
 // is bound by the latency of one thread walking cars and obstacles one after the other (issue slots 28 % busy).
 // Here lane g of an environment's group IS car g (its state stays in registers for the whole step) and owns the
 // obstacle slots g, g + G, ...; what the other lanes need of a car (position, velocity, lane, rect) is published
-// in shared memory, and the stages of a tick are separated by __syncwarp on the group's lanes.  The order-
+// in shared memory, and the stages of a tick are separated by full-mask __syncwarp (control flow is uniform over the
+// warp; a group that has finished its step just goes inactive).  The order-
 // dependent semantics of the reference survive the parallel evaluation because every cross-car read is of a
 // value whose version (before / after this tick's update) is known statically:
 //   * actions run for every car in id order (highway_core.py:280-281): maintain() of car a sees the lanes cars j < a
@@ -17,7 +18,8 @@
 //     and flags, so all cars switch first (old and new lane are both published) and then search;
 //   * cars update in id order and subtract the leader's velocity "as it is now" (agent.py:147-151): its new value
 //     for cars behind it in id order, its old value for cars before it; velocities are double-buffered;
-//   * obstacles, the leader election, spawn / retire and the collision test each read only finished values.
+//   * the leader election (moved ahead of the obstacle updates: it only reads the cars), the obstacle updates, spawn /
+//     retire and the collision test each read only finished values.
 // Scalars of the environment header (tick, leader, counters, slot bookkeeping) are replicated in the registers
 // of all G lanes and evolve identically; the serial slot bookkeeping of a spawn or a retire runs on lane 0 and is
 // broadcast with shuffles.
