@@ -124,7 +124,8 @@ int hw_sa_rollout_random(const HwSaState *state, const HwSaOut *out, const HwSim
                          int64_t n, int flags, void *stream);
 
 /* Host-buffer step: HOST actions -> device -> step -> HOST obs/rew/done, all on `stream`, returns
- * after the copies have landed.  d_actions and d_out are caller-owned DEVICE staging buffers of the
+ * after the copies have landed.  Batches of 262,144 environments and more run as two half-batch launches, the second on
+ * a stream created for the duration of the call, so that its upload and kernel overlap the first half's download.  d_actions and d_out are caller-owned DEVICE staging buffers of the
  * same shapes; h_* should be page-locked for full copy bandwidth. */
 int hw_sa_step_host(const HwSaState *state, const void *h_actions, void *d_actions, const HwSaOut *d_out,
                     float *h_obs, float *h_rew, uint8_t *h_done, const HwSimParams *params,
