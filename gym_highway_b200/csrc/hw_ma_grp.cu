@@ -27,7 +27,10 @@
 
 namespace hw {
 
-constexpr int kGrpWarps = 8;  // warps per block
+#ifndef HW_MA_WARPS
+#define HW_MA_WARPS 8
+#endif
+constexpr int kGrpWarps = HW_MA_WARPS;  // warps per block
 
 template <int G>
 struct GrpLayout {
