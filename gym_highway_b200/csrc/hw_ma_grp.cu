@@ -136,7 +136,8 @@ struct GrpStep {
     bool active;
     uint32_t done;
     int no_acc, na_acc;   // this car's collisions during the step
-    double reward, ang;
+    double ang;
+    bool last_hit;        // this car collided in the last tick that ran (its reward is then -250)
     int lead, last;
     uint32_t amask, apair, fire;
     int dlane;
@@ -144,7 +145,7 @@ struct GrpStep {
 
     __device__ __forceinline__ GrpStep(double *smem, int e, int g_, int base_, int A_, int K_)
         : sm(smem, e), g(g_), base(base_), A(AT ? AT : A_), K(K_), cur(0), active(false), done(0), no_acc(0), na_acc(0),
-          reward(0.0), ang(0.0), lead(0), last(0), amask(0), apair(0), fire(0), dlane(0), a0_5dt(0.0), a1_30dt(0.0)
+          ang(0.0), last_hit(false), lead(0), last(0), amask(0), apair(0), fire(0), dlane(0), a0_5dt(0.0), a1_30dt(0.0)
     {
         pc = sm.car + (size_t)e * G;
         pi = sm.ci + (size_t)e * G;
@@ -393,9 +394,8 @@ struct GrpStep {
         const bool is_car = g < A;
         no = is_car ? no : 0; na = is_car ? na : 0;
         no_acc += no; na_acc += na;
-        reward = dsub(ddiv_const(c.vx, 20.0), 1.0);
-        dset_if(no + na > 0, reward, -250.0);
-        return no + na > 0;
+        last_hit = no + na > 0;
+        return last_hit;
     }
 
     // Scenario.observations (simple_base.py:82-154) + MultiAgentEnv._get_obs_norm (highway_env.py:139-149) of the lane's car
@@ -560,10 +560,13 @@ ma_grp_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
     }
 
     // rewards of the step: summed in id order for shared_reward (highway_env.py:92-94) and for Monitor; collision counters
-    if (live) { st.sm.r(g) = st.reward; st.sm.crect(g) = make_int2(st.no_acc, st.na_acc); }  // the rect slot is free now
+    // Scenario.rewards of the last tick that ran (simple_base.py:65-80): -250 for a car that collided in it, else v.x / 20 - 1
+    double my_reward = dsub(ddiv_const(st.c.vx, 20.0), 1.0);
+    dset_if(st.last_hit, my_reward, -250.0);
+    if (live) { st.sm.r(g) = my_reward; st.sm.crect(g) = make_int2(st.no_acc, st.na_acc); }  // the rect slot is free now
     __syncwarp();
     if (live) {
-        double r = st.reward, rsum = 0.0;
+        double r = my_reward, rsum = 0.0;
         for (int a = 0; a < A; ++a) {
             rsum = dadd(rsum, st.sm.r(a));
             const int2 cnt = st.sm.crect(a);
