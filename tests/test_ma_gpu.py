@@ -165,3 +165,23 @@ def test_fast_mode_per_step_parity_from_identical_states(A, continuous):
             assert rel.max() <= 1e-5
             nbits += int(np.sum(a32.view(np.uint32) != b32.view(np.uint32))); nvals += a32.size
     assert nbits <= 1e-5 * nvals, "%d of %d float values differ in the last bit" % (nbits, nvals)
+
+
+def test_full_size_properties_262144_envs():
+    """sweep-size multi-agent batch: a slice equals a small batch built with the slice's global env ids, two instances agree
+    bit for bit (the lane-cooperative kernel has no scheduling dependence), observations are finite and the obstacle slots
+    never overflow"""
+    n, A, lo, m = 262144, 5, 100003, 3000
+    big, twin, part = _env(n, A, seed=23), _env(n, A, seed=23), _env(m, A, seed=23, env_id0=lo)
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    for t in range(60):
+        act = torch.where(torch.rand((n, A), generator=g, device="cuda") < 0.6, 2,
+                          torch.randint(0, 4, (n, A), generator=g, device="cuda")).to(torch.int32)
+        ob, rb, db, _ = big.step(act)
+        ot, rt, dt, _ = twin.step(act)
+        op, rp, dp, _ = part.step(act[lo:lo + m].contiguous())
+        assert torch.equal(ob, ot) and torch.equal(db, dt), t
+        assert torch.equal(ob[lo:lo + m], op) and torch.equal(rb[lo:lo + m], rp) and torch.equal(db[lo:lo + m], dp), t
+    assert bool(torch.isfinite(ob).all()) and int(big.diagnostics().max()) == 0
+    st = big.episode_statistics()
+    assert st["episodes"] > n // 2

@@ -298,3 +298,32 @@ def test_fast_mode_per_step_parity_from_identical_states(continuous):
             assert rel.max() <= REL_TOL
             nbits += int(np.sum(a32.view(np.uint32) != b32.view(np.uint32))); nvals += a32.size
     assert nbits <= 1e-6 * nvals, "%d of %d float values differ in the last bit" % (nbits, nvals)
+
+
+def test_full_size_properties_4m_envs():
+    """BASELINE-size batch (4,194,304 envs, the bench workload): properties that do not need the oracle.
+    * a slice of the big batch equals a small batch constructed with the slice's global env ids (what sharding relies on:
+      an env's trajectory depends only on seed, global id and its actions);
+    * two instances agree bit for bit (no race, no dependence on scheduling);
+    * observations are normalised into [0, 1]; the device episode counters add up."""
+    n, lo, m = 1 << 22, 1234567 & ~1, 4096
+    big, twin, part = _env(n, seed=17), _env(n, seed=17), _env(m, seed=17, env_id0=lo)
+    for k in range(3):                      # 3 x 90 steps: first time-outs at step 240, plenty of crashes before
+        ob, rb, db = big.rollout_random(90, action_ctr0=90 * k)
+        ot, rt, dt = twin.rollout_random(90, action_ctr0=90 * k)
+        op, rp, dp = part.rollout_random(90, action_ctr0=90 * k)
+    assert torch.equal(ob, ot) and torch.equal(rb, rt) and torch.equal(db, dt)
+    assert torch.equal(ob[lo:lo + m], op) and torch.equal(rb[lo:lo + m], rp) and torch.equal(db[lo:lo + m], dp)
+    sb, sp = big.state_dict(), part.state_dict()
+    assert torch.equal(sb["car_a"][lo:lo + m], sp["car_a"]) and torch.equal(sb["obst"][:, lo:lo + m], sp["obst"])
+    assert float(ob.min()) >= 0.0 and float(ob.max()) <= 1.0 and bool(torch.isfinite(rb).all())
+    # a python step on top: random actions from a tensor, same comparison through the ordinary step() entry point
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    act = torch.randint(0, 4, (n,), generator=g, device="cuda", dtype=torch.int32)
+    ob, rb, db, _ = big.step(act)
+    op, rp, dp, _ = part.step(act[lo:lo + m].contiguous())
+    assert torch.equal(ob[lo:lo + m], op) and torch.equal(db[lo:lo + m], dp)
+    st = big.episode_statistics()
+    assert st["episodes"] > n and st["timeouts"] > 0 and st["obs_collisions"] >= st["episodes"] - st["timeouts"]
+    assert 1.0 <= st["mean_length"] <= 240.0
+
