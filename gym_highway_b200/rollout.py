@@ -75,6 +75,21 @@ class MlpPolicy(nn.Module):
         return out[:, :self._n_head - 1], out[:, self._n_head - 1]
 
     @torch.no_grad()
+    def head_bf16(self, obs):
+        """[N, 8k] bfloat16: the logits (or means), then the value, then zero padding - the merged head GEMM's output as it
+        is, for consumers that read it in place (hw_policy_sample_discrete)"""
+        body, hw, hb = self._bf16_weights()
+        k0 = body[0][0].shape[0]
+        if obs.shape[1] == k0:
+            h = obs.to(torch.bfloat16)
+        else:
+            h = obs.new_zeros((obs.shape[0], k0), dtype=torch.bfloat16)
+            h[:, :obs.shape[1]] = obs
+        for w, b in body:
+            h = torch._addmm_activation(b, h, w, use_gelu=False)
+        return torch.addmm(hb, h, hw)
+
+    @torch.no_grad()
     def step(self, obs, generator=None):
         """actions, values, neglogpacs — the triple `model.step` returns in ppo2 (runner.py:33)"""
         out, v = self.forward(obs)
@@ -243,3 +258,71 @@ class A2CRunner(object):
         if self.gamma > 0.0:
             rewards = discount_with_dones(self.mb_rewards, dones, self.gamma, bootstrap=self.model.value(self.obs))
         return sf01(self.mb_obs), None, sf01(rewards), sf01(masks), sf01(self.mb_actions), sf01(self.mb_values)
+
+
+class DeviceRunner(object):
+    """ppo2's Runner (baselines/ppo2/runner.py:20-66) for a discrete-action `HighwayVecEnv`, with nothing between the policy's
+    GEMMs and the env kernel but ONE launch: `hw_policy_sample_discrete` turns the merged head's output into actions, values
+    and neglogpacs written in place into the rollout's [T, N] buffers, and the env step writes the next observation, the
+    reward and the done flag straight into theirs (`step_into`) - no per-step copies, casts or elementwise torch kernels.
+    `run()` returns what `Runner.run(want_epinfos=False)` returns; `run_graphed()` replays the rollout from one CUDA graph.
+    Actions are sampled from a Philox stream keyed by (seed, global env id, step counter), so a rollout is reproducible
+    and independent of how the envs are sharded over GPUs."""
+
+    def __init__(self, env, model, nsteps, gamma=0.99, lam=0.95, seed=0):
+        if getattr(env, "continuous", False):
+            raise ValueError("DeviceRunner samples categorical actions; use Runner for the continuous env")
+        from . import _lib
+        self._libmod, self._lib = _lib, _lib.load()
+        self.env, self.model, self.nsteps, self.gamma, self.lam = env, model, nsteps, gamma, lam
+        self.seed = int(seed) & (2 ** 64 - 1)
+        n, dev = env.num_envs, env.device
+        self.n_actions = model.pi.out_features
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)   # steps sampled so far (device side: survives graph replay)
+        self.mb_obs = torch.empty(nsteps + 1, n, 18, dtype=torch.float32, device=dev)   # row t: what the policy saw at step t
+        self.mb_done_u8 = torch.zeros(nsteps + 1, n, dtype=torch.uint8, device=dev)      # row t: episode ended BEFORE step t
+        self.mb_rewards = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
+        self.mb_actions = torch.empty(nsteps, n, dtype=torch.int32, device=dev)
+        self.mb_values = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
+        self.mb_neglogpacs = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
+        self.mb_obs[nsteps].copy_(env.reset())
+        self._graph = None
+
+    def _sample(self, head, t):
+        import ctypes as C
+        stream = C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
+        with torch.cuda.device(self.env.device):
+            rc = self._lib.hw_policy_sample_discrete(
+                C.c_void_p(head.data_ptr()), 1 if head.dtype == torch.bfloat16 else 0, head.shape[1], self.n_actions,
+                self.seed, self.env._env_id0, t, C.c_void_p(self.step_counter.data_ptr()), C.c_void_p(self.mb_actions[t].data_ptr()),
+                C.c_void_p(self.mb_neglogpacs[t].data_ptr()), C.c_void_p(self.mb_values[t].data_ptr()), head.shape[0], stream)
+        self._libmod.check(rc, "hw_policy_sample_discrete")
+
+    @torch.no_grad()
+    def run(self):
+        T = self.nsteps
+        # the last observation / done row of the previous rollout is the first of this one
+        self.mb_obs[0].copy_(self.mb_obs[T])
+        self.mb_done_u8[0].copy_(self.mb_done_u8[T])
+        for t in range(T):
+            self._sample(self.model.head_bf16(self.mb_obs[t]), t)
+            self.env.step_into(self.mb_actions[t], self.mb_obs[t + 1], self.mb_rewards[t], self.mb_done_u8[t + 1])
+        self.step_counter += T
+        dones = self.mb_done_u8.to(torch.float32)
+        last_values = self.model.value(self.mb_obs[T])
+        returns, _ = gae(self.mb_rewards, self.mb_values, dones[:T], last_values, dones[T], self.gamma, self.lam)
+        return (sf01(self.mb_obs[:T]), sf01(returns), sf01(dones[:T]), sf01(self.mb_actions), sf01(self.mb_values),
+                sf01(self.mb_neglogpacs), None, [])
+
+    @torch.no_grad()
+    def run_graphed(self):
+        """`run()` replayed from one CUDA graph (captured on the first call, after an eager warm-up rollout); the returned
+        tensors live in the graph's memory pool and are overwritten by the next call"""
+        if self._graph is None:
+            self.run()
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._g_out = self.run()[:7]
+        self._graph.replay()
+        return self._g_out + ([],)

@@ -279,6 +279,19 @@ class HighwayVecEnv(VecEnv):
         infos = LazyInfos(self.num_envs, self._make_info_fetcher(out))
         return self._wrap(out['obs']), self._wrap(out['rew']), self._wrap(out['done'], True), infos
 
+    def step_into(self, actions, obs, rew, done):
+        """step() with caller-provided output tensors (float32 [N, 18], float32 [N], uint8 [N] on this device, contiguous):
+        the kernel writes the post-step observation, reward and done flag straight into them - e.g. rows of a rollout's
+        [T, N] buffers - instead of the env's own double-buffered outputs.  `actions` must already be an int32 [N]
+        (float32 [N, 2] when continuous) tensor on this device.  Asynchronous; no infos (use episode_statistics())."""
+        assert not self.closed and self._pending is None
+        out = _lib.HwSaOut(obs.data_ptr(), rew.data_ptr(), done.data_ptr(), self._out[0]['term'].data_ptr(),
+                           self.stats.data_ptr() if self.stats is not None else 0)
+        with torch.cuda.device(self.device):
+            rc = self._lib.hw_sa_step(C.byref(self._state_c), _as_ptr(actions), C.byref(out), C.byref(self.params),
+                                      self._seed, self._env_id0, self.num_envs, self._flags, self._stream())
+        _lib.check(rc, "hw_sa_step")
+
     def rollout_random(self, steps, action_ctr0=0):
         """`steps` env.steps with in-kernel uniform random actions in one launch (benchmark / warm-up);
         returns the last step's (obs, rew, done)"""

@@ -182,6 +182,19 @@ int hw_ma_step_host(const HwMaState *state, const void *h_actions, void *d_actio
                     float *h_obs, float *h_rew, uint8_t *h_done, const HwSimParams *params,
                     uint64_t seed, uint64_t env_id0, int64_t n, int flags, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Rollout collection (consumer side; baselines/ppo2/runner.py:33, baselines/common/distributions.py CategoricalPd).
+ * The tail of model.step for a categorical policy in ONE launch: per row, log-softmax over the first `n_actions` entries of
+ * `head` (float32, or bfloat16 when head_is_bf16), one sample by inverse CDF on a Philox uniform keyed by
+ * (seed, env_id0 + row, counter + *counter_offset), its negative log-probability, and the value (entry n_actions of the
+ * row).  `counter_offset` (nullable) is a DEVICE counter the caller advances between rollouts, so that a CUDA graph holding
+ * a whole rollout draws fresh numbers on every replay.  `stride` = elements per row of `head` (>= n_actions + 1).  Outputs
+ * may point into [T, N] rollout buffers. */
+#define HW_POLICY_MAX_ACTIONS 8
+int hw_policy_sample_discrete(const void *head, int head_is_bf16, int stride, int n_actions, uint64_t seed,
+                              uint64_t env_id0, uint64_t counter, const unsigned long long *counter_offset,
+                              int32_t *actions, float *neglogp, float *values, int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

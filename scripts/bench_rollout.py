@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=131072)
 ap.add_argument("--nsteps", type=int, default=240)
 ap.add_argument("--rollouts", type=int, default=3)
+ap.add_argument("--runner", default="device", choices=["device", "torch"], help="device: fused sampling kernel + zero-copy buffers (DeviceRunner); torch: Runner")
 ap.add_argument("--eager", action="store_true", help="issue every launch from the host instead of replaying one CUDA graph per rollout")
 args = ap.parse_args()
 world, rank, lr = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -23,13 +24,17 @@ dev = torch.device("cuda", lr)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 from gym_highway_b200 import HighwayVecEnv
-from gym_highway_b200.rollout import MlpPolicy, Runner
+from gym_highway_b200.rollout import MlpPolicy, Runner, DeviceRunner
 torch.manual_seed(0)
 env = HighwayVecEnv(args.envs, seed=0, device=dev, env_id0=rank * args.envs)
 pol = MlpPolicy(18, 4, bf16_inference=True).to(dev)
 torch.cuda.manual_seed(rank)
-run = Runner(env, pol, nsteps=args.nsteps, gamma=0.99, lam=0.95, generator=None)
-collect = (lambda: run.run(want_epinfos=False)) if args.eager else run.run_graphed
+if args.runner == "device":
+    run = DeviceRunner(env, pol, nsteps=args.nsteps, gamma=0.99, lam=0.95, seed=rank)
+    collect = run.run if args.eager else run.run_graphed
+else:
+    run = Runner(env, pol, nsteps=args.nsteps, gamma=0.99, lam=0.95, generator=None)
+    collect = (lambda: run.run(want_epinfos=False)) if args.eager else run.run_graphed
 collect()  # warm-up rollout (and graph capture)
 torch.cuda.synchronize()
 if world > 1:
@@ -47,7 +52,7 @@ if world > 1:
 if rank == 0:
     total = world * args.envs * args.nsteps * args.rollouts
     print(json.dumps({"workload": "ppo2 rollout collection, %d envs/GPU x %d GPU(s), T=%d, MLP 18-256-256-256 policy on device" % (args.envs, world, args.nsteps),
-                      "mode": "eager" if args.eager else "cuda graph", "rollout_env_steps_per_s": total / (ms * 1e-3), "ms_per_rollout": ms / args.rollouts,
+                      "runner": args.runner, "mode": "eager" if args.eager else "cuda graph", "rollout_env_steps_per_s": total / (ms * 1e-3), "ms_per_rollout": ms / args.rollouts,
                       "rollout_buffer_GB_per_gpu": args.nsteps * args.envs * 18 * 4 / 1e9, "last_rollout_episodes": stats}))
 if world > 1:
     dist.barrier(); dist.destroy_process_group()

@@ -59,6 +59,54 @@ def test_graphed_rollout_replays_real_transitions():
         Runner(HighwayVecEnv(8, seed=1), pol, nsteps=3, generator=None).run_graphed()
 
 
+@pytest.mark.parametrize("graphed", [False, True])
+def test_device_runner_zero_copy_rollout(graphed):
+    """DeviceRunner: fused sampling kernel + env outputs written straight into the [T, N] buffers; the stored transitions are
+    the env's own, the stored values / neglogpacs are the policy's, fresh actions on every rollout (also under graph replay)"""
+    from gym_highway_b200 import HighwayVecEnv
+    from gym_highway_b200.rollout import MlpPolicy, DeviceRunner, gae, sf01
+    torch.manual_seed(0)
+    n, T = 2048, 12
+    pol = MlpPolicy(18, 4).cuda()
+    run = DeviceRunner(HighwayVecEnv(n, seed=4), pol, nsteps=T, seed=9)
+    collect = run.run_graphed if graphed else run.run
+    first = [x.clone() for x in collect()[:6]]
+    snapshot = {k: v.clone() for k, v in run.env.state_dict().items()}
+    start_obs = run.mb_obs[T].clone()
+    obs, returns, masks, actions, values, neglogp = [x.clone() for x in collect()[:6]]
+    assert obs.shape == (n * T, 18) and actions.dtype == torch.int32 and actions.min() >= 0 and actions.max() <= 3
+    assert not torch.equal(first[3], actions)           # new random numbers on every rollout
+    o, a = obs.reshape(n, T, 18), actions.reshape(n, T)
+    assert torch.equal(o[:, 0, :], start_obs)
+    ref = HighwayVecEnv(n, seed=4)
+    ref.load_state_dict(snapshot)
+    rews, dones = [], []
+    for t in range(T):
+        ob, r, d, _ = ref.step(a[:, t].contiguous())
+        rews.append(r.clone()); dones.append(d.clone())
+        if t + 1 < T:
+            assert torch.equal(ob, o[:, t + 1, :]), t
+    # values / neglogpacs: the policy's own, from the same bf16 head
+    with torch.no_grad():
+        head = pol.head_bf16(obs).float()
+    logp = torch.log_softmax(head[:, :4], dim=-1)
+    assert torch.allclose(values, head[:, 4], atol=1e-6)
+    assert torch.allclose(neglogp, -logp.gather(1, actions.long().unsqueeze(1)).squeeze(1), atol=2e-3)
+    # masks: episode ended before step t; returns: GAE over the env's rewards
+    m = masks.reshape(n, T)
+    for t in range(1, T):
+        assert torch.equal(m[:, t] > 0.5, dones[t - 1])
+    R = torch.stack(rews)                                   # [T, N]
+    with torch.no_grad():
+        last_v = pol.value(ref._out[ref._cur]["obs"])
+    D = torch.cat([m.t(), dones[-1].float().unsqueeze(0)], 0)
+    want, _ = gae(R, values.reshape(n, T).t().contiguous(), D[:T], last_v, D[T], 0.99, 0.95)
+    assert torch.allclose(returns, sf01(want), atol=1e-3)
+    # the sampler follows the policy: empirical frequency of each action vs the mean probability
+    freq = torch.bincount(actions.long(), minlength=4).double() / actions.numel()
+    assert (freq - logp.exp().double().mean(0)).abs().max() < 0.02
+
+
 def test_vec_monitor_on_the_real_env(tmp_path):
     from gym_highway_b200 import HighwayVecEnv
     from gym_highway_b200.monitor import VecMonitor, load_results
