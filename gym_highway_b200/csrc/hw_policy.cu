@@ -4,6 +4,7 @@
 //
 // Eagerly in torch this is a dozen small launches per step (log_softmax, exp, running sums, compares, gather, casts,
 // copies) - a quarter of a rollout step at 10^5 environments once the env step itself takes 16 us.
+#include <cuda_bf16.h>
 #include "hw_common.cuh"
 #include "../../include/highway_b200.h"
 
@@ -58,7 +59,30 @@ policy_sample_discrete_kernel(const T *__restrict__ head, const int stride, cons
     values[i] = to_f32<T>(row[n_actions]);
 }
 
+// float32 [n][cols] -> bfloat16 [n][dst_cols], zero padded on the right (round to nearest even): the first GEMM of the policy wants
+// its K dimension aligned to 8 elements, the observation has 18 columns
+__global__ void __launch_bounds__(256)
+cast_pad_bf16_kernel(const float *__restrict__ src, const int cols, unsigned short *__restrict__ dst, const int dst_cols, const int64_t total)
+{
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;  // one thread per pair of output elements
+    if (2 * j >= total) return;
+    const int64_t row = (2 * j) / dst_cols;
+    const int col = (int)((2 * j) - row * dst_cols);  // dst_cols is even, so a pair never straddles rows
+    const float a = (col < cols) ? src[row * cols + col] : 0.f, b = (col + 1 < cols) ? src[row * cols + col + 1] : 0.f;
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    reinterpret_cast<__nv_bfloat162 *>(dst)[j] = v;
+}
+
 }  // namespace hw
+
+extern "C" int hw_cast_pad_bf16(const float *src, int cols, void *dst, int dst_cols, int64_t n, void *stream)
+{
+    if (!src || !dst || n <= 0 || cols < 1 || dst_cols < cols || (dst_cols & 1)) return HW_E_BADARG;
+    const int64_t total = n * dst_cols;
+    const unsigned grid = (unsigned)((total / 2 + 255) / 256);
+    hw::cast_pad_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, cols, static_cast<unsigned short *>(dst), dst_cols, total);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int hw_policy_sample_discrete(const void *head, int head_is_bf16, int stride, int n_actions, uint64_t seed,
                                          uint64_t env_id0, uint64_t counter, const unsigned long long *counter_offset,

@@ -80,7 +80,16 @@ class MlpPolicy(nn.Module):
         is, for consumers that read it in place (hw_policy_sample_discrete)"""
         body, hw, hb = self._bf16_weights()
         k0 = body[0][0].shape[0]
-        if obs.shape[1] == k0:
+        if obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous():
+            # one launch for cast + pad (zero-fill + strided copy are two, and the strided one is slow)
+            import ctypes as C
+            from . import _lib
+            h = torch.empty((obs.shape[0], k0), dtype=torch.bfloat16, device=obs.device)
+            with torch.cuda.device(obs.device):
+                rc = _lib.load().hw_cast_pad_bf16(C.c_void_p(obs.data_ptr()), obs.shape[1], C.c_void_p(h.data_ptr()), k0, obs.shape[0],
+                                                  C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream))
+            _lib.check(rc, "hw_cast_pad_bf16")
+        elif obs.shape[1] == k0:
             h = obs.to(torch.bfloat16)
         else:
             h = obs.new_zeros((obs.shape[0], k0), dtype=torch.bfloat16)

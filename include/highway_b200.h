@@ -190,6 +190,10 @@ int hw_ma_step_host(const HwMaState *state, const void *h_actions, void *d_actio
  * row).  `counter_offset` (nullable) is a DEVICE counter the caller advances between rollouts, so that a CUDA graph holding
  * a whole rollout draws fresh numbers on every replay.  `stride` = elements per row of `head` (>= n_actions + 1).  Outputs
  * may point into [T, N] rollout buffers. */
+/* float32 [n][cols] -> bfloat16 [n][dst_cols] (dst_cols even, >= cols), zero padded on the right: the policy's first GEMM wants its
+ * K dimension aligned, the observation has 18 columns. */
+int hw_cast_pad_bf16(const float *src, int cols, void *dst, int dst_cols, int64_t n, void *stream);
+
 #define HW_POLICY_MAX_ACTIONS 8
 int hw_policy_sample_discrete(const void *head, int head_is_bf16, int stride, int n_actions, uint64_t seed,
                               uint64_t env_id0, uint64_t counter, const unsigned long long *counter_offset,
