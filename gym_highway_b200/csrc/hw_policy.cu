@@ -73,7 +73,41 @@ cast_pad_bf16_kernel(const float *__restrict__ src, const int cols, unsigned sho
     reinterpret_cast<__nv_bfloat162 *>(dst)[j] = v;
 }
 
+// Generalised advantage estimation exactly as ppo2's runner computes it (baselines/ppo2/runner.py:53-65), one thread per
+// environment walking its T steps backwards; all arrays are [T][n] (step major), so a warp reads 32 neighbouring floats per step.
+//   dones[t]  (t < T): the episode ended on the transition BEFORE step t;  dones[T]: after the last step
+//   delta = r[t] + gamma * V[t+1] * (1 - dones[t+1]) - V[t];  A[t] = delta + gamma * lam * (1 - dones[t+1]) * A[t+1]
+__global__ void __launch_bounds__(256)
+gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values, const uint8_t *__restrict__ dones,
+           const float *__restrict__ last_values, const float gamma, const float lam, float *__restrict__ returns,
+           float *__restrict__ advantages, const int T, const int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float nextvalue = last_values[i], lastgaelam = 0.f;
+    float nextnonterminal = 1.0f - (float)dones[(int64_t)T * n + i];
+    for (int t = T - 1; t >= 0; --t) {
+        const float v = values[(int64_t)t * n + i];
+        // the same association order as the runner's numpy expressions (float32 throughout)
+        const float delta = __fsub_rn(__fadd_rn(rewards[(int64_t)t * n + i], __fmul_rn(__fmul_rn(gamma, nextvalue), nextnonterminal)), v);
+        lastgaelam = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(gamma, lam), nextnonterminal), lastgaelam));
+        if (advantages) advantages[(int64_t)t * n + i] = lastgaelam;
+        returns[(int64_t)t * n + i] = __fadd_rn(lastgaelam, v);
+        nextvalue = v;
+        nextnonterminal = 1.0f - (float)dones[(int64_t)t * n + i];
+    }
+}
+
 }  // namespace hw
+
+extern "C" int hw_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_values, float gamma,
+                      float lam, float *returns, float *advantages, int T, int64_t n, void *stream)
+{
+    if (!rewards || !values || !dones || !last_values || !returns || T < 1 || n <= 0) return HW_E_BADARG;
+    hw::gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, gamma, lam, returns,
+                                                                                  advantages, T, n);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int hw_cast_pad_bf16(const float *src, int cols, void *dst, int dst_cols, int64_t n, void *stream)
 {

@@ -318,8 +318,16 @@ class DeviceRunner(object):
             self.env.step_into(self.mb_actions[t], self.mb_obs[t + 1], self.mb_rewards[t], self.mb_done_u8[t + 1])
         self.step_counter += T
         dones = self.mb_done_u8.to(torch.float32)
-        last_values = self.model.value(self.mb_obs[T])
-        returns, _ = gae(self.mb_rewards, self.mb_values, dones[:T], last_values, dones[T], self.gamma, self.lam)
+        last_values = self.model.value(self.mb_obs[T]).contiguous()
+        # GAE in one launch (the torch loop is 8 small kernels per step: a fifth of the rollout at T = 240)
+        import ctypes as C
+        returns = torch.empty_like(self.mb_rewards)
+        with torch.cuda.device(self.env.device):
+            rc = self._lib.hw_gae(C.c_void_p(self.mb_rewards.data_ptr()), C.c_void_p(self.mb_values.data_ptr()),
+                                  C.c_void_p(self.mb_done_u8.data_ptr()), C.c_void_p(last_values.data_ptr()), self.gamma, self.lam,
+                                  C.c_void_p(returns.data_ptr()), None, T, self.env.num_envs,
+                                  C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream))
+        self._libmod.check(rc, "hw_gae")
         return (sf01(self.mb_obs[:T]), sf01(returns), sf01(dones[:T]), sf01(self.mb_actions), sf01(self.mb_values),
                 sf01(self.mb_neglogpacs), None, [])
 

@@ -194,6 +194,12 @@ int hw_ma_step_host(const HwMaState *state, const void *h_actions, void *d_actio
  * K dimension aligned, the observation has 18 columns. */
 int hw_cast_pad_bf16(const float *src, int cols, void *dst, int dst_cols, int64_t n, void *stream);
 
+/* GAE(gamma, lam) of ppo2's runner (baselines/ppo2/runner.py:53-65) over step-major [T][n] buffers in one launch:
+ * dones is uint8 [T + 1][n] (row t: the episode ended before step t; row T: after the last step), last_values [n] the value
+ * of the state after the last step.  Writes returns = advantages + values, and the advantages when `advantages` is non-NULL. */
+int hw_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_values, float gamma, float lam,
+           float *returns, float *advantages, int T, int64_t n, void *stream);
+
 #define HW_POLICY_MAX_ACTIONS 8
 int hw_policy_sample_discrete(const void *head, int head_is_bf16, int stride, int n_actions, uint64_t seed,
                               uint64_t env_id0, uint64_t counter, const unsigned long long *counter_offset,
