@@ -107,6 +107,46 @@ def test_device_runner_zero_copy_rollout(graphed):
     assert (freq - logp.exp().double().mean(0)).abs().max() < 0.02
 
 
+def test_gae_and_cast_kernels_match_torch():
+    import ctypes as C
+    from gym_highway_b200 import _lib
+    from gym_highway_b200.rollout import gae
+    lib = _lib.load()
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    T, n = 37, 5001
+    rew = torch.randn(T, n, generator=g, device="cuda")
+    val = torch.randn(T, n, generator=g, device="cuda")
+    done = (torch.rand(T + 1, n, generator=g, device="cuda") < 0.1).to(torch.uint8)
+    last = torch.randn(n, generator=g, device="cuda")
+    ret, adv = torch.empty_like(rew), torch.empty_like(rew)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.hw_gae(C.c_void_p(rew.data_ptr()), C.c_void_p(val.data_ptr()), C.c_void_p(done.data_ptr()), C.c_void_p(last.data_ptr()),
+                    0.99, 0.95, C.c_void_p(ret.data_ptr()), C.c_void_p(adv.data_ptr()), T, n, stream)
+    assert rc == 0
+    d = done.float()
+    want_ret, want_adv = gae(rew, val, d[:T], last, d[T], 0.99, 0.95)
+    assert torch.allclose(adv, want_adv, rtol=1e-5, atol=1e-5) and torch.allclose(ret, want_ret, rtol=1e-5, atol=1e-5)
+    # cast + pad
+    x = torch.randn(777, 18, generator=g, device="cuda")
+    y = torch.empty(777, 24, dtype=torch.bfloat16, device="cuda")
+    assert lib.hw_cast_pad_bf16(C.c_void_p(x.data_ptr()), 18, C.c_void_p(y.data_ptr()), 24, 777, stream) == 0
+    assert torch.equal(y[:, :18], x.to(torch.bfloat16)) and bool((y[:, 18:] == 0).all())
+    # the sampler: frequencies of a fixed distribution, float32 and bfloat16 heads
+    probs = torch.tensor([0.05, 0.15, 0.3, 0.5], device="cuda")
+    for dt in (torch.float32, torch.bfloat16):
+        head = torch.zeros(200000, 8, dtype=dt, device="cuda")
+        head[:, :4] = probs.log().to(dt)
+        head[:, 4] = 1.5
+        a = torch.empty(200000, dtype=torch.int32, device="cuda"); nl = torch.empty(200000, device="cuda"); v = torch.empty(200000, device="cuda")
+        rc = lib.hw_policy_sample_discrete(C.c_void_p(head.data_ptr()), int(dt == torch.bfloat16), 8, 4, 7, 0, 3, None,
+                                           C.c_void_p(a.data_ptr()), C.c_void_p(nl.data_ptr()), C.c_void_p(v.data_ptr()), 200000, stream)
+        assert rc == 0
+        p = torch.softmax(head[:, :4].float(), -1)[0]
+        freq = torch.bincount(a.long(), minlength=4).float() / a.numel()
+        assert (freq - p).abs().max() < 5e-3 and bool((v == 1.5).all())
+        assert torch.allclose(nl, -p.log()[a.long()], atol=1e-5)
+
+
 def test_vec_monitor_on_the_real_env(tmp_path):
     from gym_highway_b200 import HighwayVecEnv
     from gym_highway_b200.monitor import VecMonitor, load_results
