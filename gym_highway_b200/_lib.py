@@ -67,6 +67,8 @@ _EXPORTS = {
     "hw_ma_step_host": (C.c_int, [C.POINTER(HwMaState), C.c_void_p, C.c_void_p, C.POINTER(HwMaOut),
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HwSimParams),
                                   C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
+    "hw_policy_sample_gaussian2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hw_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
                          C.c_int64, C.c_void_p]),
     "hw_cast_pad_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),

@@ -73,6 +73,39 @@ cast_pad_bf16_kernel(const float *__restrict__ src, const int cols, unsigned sho
     reinterpret_cast<__nv_bfloat162 *>(dst)[j] = v;
 }
 
+// The same for a diagonal Gaussian policy (DiagGaussianPd): a = mean + exp(logstd) * N(0, 1) with the normals from Box-Muller
+// on two Philox uniforms per pair, neglogp = 0.5 * sum(((a - mean) / std)^2) + 0.5 * log(2 pi) * d + sum(logstd); the
+// unclipped sample is stored for the learner, its clamp to [-1, 1] is what the env acts on.
+// head[i * stride + k], k < 2: means; head[i * stride + 2]: value
+template <typename T>
+__global__ void __launch_bounds__(256)
+policy_sample_gaussian2_kernel(const T *__restrict__ head, const int stride, const float *__restrict__ logstd,
+                               const uint64_t seed, const uint64_t env_id0, const uint64_t counter0,
+                               const unsigned long long *__restrict__ counter_offset, float2 *__restrict__ actions,
+                               float2 *__restrict__ env_actions, float *__restrict__ neglogp, float *__restrict__ values, const int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t counter = counter0 + (counter_offset ? (uint64_t)*counter_offset : 0ull);
+    const T *row = head + i * stride;
+    const float logstd0 = logstd[0], logstd1 = logstd[1];  // a trained parameter: read on the device, also under graph replay
+    const float m0 = to_f32<T>(row[0]), m1 = to_f32<T>(row[1]);
+    const uint64_t id = env_id0 + (uint64_t)i;
+    const uint4 w = philox4x32_10(make_uint4((uint32_t)counter, (uint32_t)id, (uint32_t)(id >> 32), kPolicyTag ^ (uint32_t)(counter >> 32)),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u1 = ((float)(w.x >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
+    const float u2 = (float)(w.y >> 8) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    const float z0 = r * cs, z1 = r * sn;
+    const float a0 = m0 + expf(logstd0) * z0, a1 = m1 + expf(logstd1) * z1;
+    actions[i] = make_float2(a0, a1);
+    env_actions[i] = make_float2(fminf(fmaxf(a0, -1.f), 1.f), fminf(fmaxf(a1, -1.f), 1.f));
+    neglogp[i] = 0.5f * (z0 * z0 + z1 * z1) + 1.8378770664093453f + logstd0 + logstd1;
+    values[i] = to_f32<T>(row[2]);
+}
+
 // Generalised advantage estimation exactly as ppo2's runner computes it (baselines/ppo2/runner.py:53-65), one thread per
 // environment walking its T steps backwards; all arrays are [T][n] (step major), so a warp reads 32 neighbouring floats per step.
 //   dones[t]  (t < T): the episode ended on the transition BEFORE step t;  dones[T]: after the last step
@@ -106,6 +139,23 @@ extern "C" int hw_gae(const float *rewards, const float *values, const uint8_t *
     if (!rewards || !values || !dones || !last_values || !returns || T < 1 || n <= 0) return HW_E_BADARG;
     hw::gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, gamma, lam, returns,
                                                                                   advantages, T, n);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hw_policy_sample_gaussian2(const void *head, int head_is_bf16, int stride, const float *logstd, uint64_t seed,
+                                          uint64_t env_id0, uint64_t counter, const unsigned long long *counter_offset,
+                                          float *actions, float *env_actions, float *neglogp, float *values, int64_t n, void *stream)
+{
+    if (!head || !logstd || !actions || !env_actions || !neglogp || !values || n <= 0 || stride < 3) return HW_E_BADARG;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    float2 *a = reinterpret_cast<float2 *>(actions), *e = reinterpret_cast<float2 *>(env_actions);
+    if (head_is_bf16)
+        hw::policy_sample_gaussian2_kernel<unsigned short><<<grid, 256, 0, s>>>(static_cast<const unsigned short *>(head), stride, logstd,
+                                                                                 seed, env_id0, counter, counter_offset, a, e, neglogp, values, n);
+    else
+        hw::policy_sample_gaussian2_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(head), stride, logstd, seed, env_id0,
+                                                                        counter, counter_offset, a, e, neglogp, values, n);
     return (int)cudaGetLastError();
 }
 

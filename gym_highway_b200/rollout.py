@@ -270,8 +270,8 @@ class A2CRunner(object):
 
 
 class DeviceRunner(object):
-    """ppo2's Runner (baselines/ppo2/runner.py:20-66) for a discrete-action `HighwayVecEnv`, with nothing between the policy's
-    GEMMs and the env kernel but ONE launch: `hw_policy_sample_discrete` turns the merged head's output into actions, values
+    """ppo2's Runner (baselines/ppo2/runner.py:20-66) for a `HighwayVecEnv` (discrete or continuous), with nothing between the policy's
+    GEMMs and the env kernel but ONE launch: `hw_policy_sample_discrete` / `hw_policy_sample_gaussian2` turns the merged head's output into actions, values
     and neglogpacs written in place into the rollout's [T, N] buffers, and the env step writes the next observation, the
     reward and the done flag straight into theirs (`step_into`) - no per-step copies, casts or elementwise torch kernels.
     `run()` returns what `Runner.run(want_epinfos=False)` returns; `run_graphed()` replays the rollout from one CUDA graph.
@@ -279,8 +279,9 @@ class DeviceRunner(object):
     and independent of how the envs are sharded over GPUs."""
 
     def __init__(self, env, model, nsteps, gamma=0.99, lam=0.95, seed=0):
-        if getattr(env, "continuous", False):
-            raise ValueError("DeviceRunner samples categorical actions; use Runner for the continuous env")
+        self.continuous = bool(getattr(env, "continuous", False))
+        if self.continuous != bool(model.continuous):
+            raise ValueError("policy and env disagree on the action space")
         from . import _lib
         self._libmod, self._lib = _lib, _lib.load()
         self.env, self.model, self.nsteps, self.gamma, self.lam = env, model, nsteps, gamma, lam
@@ -291,7 +292,9 @@ class DeviceRunner(object):
         self.mb_obs = torch.empty(nsteps + 1, n, 18, dtype=torch.float32, device=dev)   # row t: what the policy saw at step t
         self.mb_done_u8 = torch.zeros(nsteps + 1, n, dtype=torch.uint8, device=dev)      # row t: episode ended BEFORE step t
         self.mb_rewards = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
-        self.mb_actions = torch.empty(nsteps, n, dtype=torch.int32, device=dev)
+        self.mb_actions = (torch.empty(nsteps, n, 2, dtype=torch.float32, device=dev) if self.continuous
+                           else torch.empty(nsteps, n, dtype=torch.int32, device=dev))
+        self.env_actions = torch.empty(n, 2, dtype=torch.float32, device=dev) if self.continuous else None  # clamped to [-1, 1]
         self.mb_values = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
         self.mb_neglogpacs = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
         self.mb_obs[nsteps].copy_(env.reset())
@@ -299,13 +302,21 @@ class DeviceRunner(object):
 
     def _sample(self, head, t):
         import ctypes as C
+        p = lambda x: C.c_void_p(x.data_ptr())
         stream = C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
+        bf16 = 1 if head.dtype == torch.bfloat16 else 0
         with torch.cuda.device(self.env.device):
-            rc = self._lib.hw_policy_sample_discrete(
-                C.c_void_p(head.data_ptr()), 1 if head.dtype == torch.bfloat16 else 0, head.shape[1], self.n_actions,
-                self.seed, self.env._env_id0, t, C.c_void_p(self.step_counter.data_ptr()), C.c_void_p(self.mb_actions[t].data_ptr()),
-                C.c_void_p(self.mb_neglogpacs[t].data_ptr()), C.c_void_p(self.mb_values[t].data_ptr()), head.shape[0], stream)
-        self._libmod.check(rc, "hw_policy_sample_discrete")
+            if self.continuous:
+                rc = self._lib.hw_policy_sample_gaussian2(p(head), bf16, head.shape[1], p(self.model.logstd.detach()), self.seed,
+                                                          self.env._env_id0, t, p(self.step_counter), p(self.mb_actions[t]),
+                                                          p(self.env_actions), p(self.mb_neglogpacs[t]), p(self.mb_values[t]),
+                                                          head.shape[0], stream)
+            else:
+                rc = self._lib.hw_policy_sample_discrete(p(head), bf16, head.shape[1], self.n_actions, self.seed, self.env._env_id0, t,
+                                                         p(self.step_counter), p(self.mb_actions[t]), p(self.mb_neglogpacs[t]),
+                                                         p(self.mb_values[t]), head.shape[0], stream)
+        self._libmod.check(rc, "hw_policy_sample")
+        return self.env_actions if self.continuous else self.mb_actions[t]
 
     @torch.no_grad()
     def run(self):
@@ -314,8 +325,8 @@ class DeviceRunner(object):
         self.mb_obs[0].copy_(self.mb_obs[T])
         self.mb_done_u8[0].copy_(self.mb_done_u8[T])
         for t in range(T):
-            self._sample(self.model.head_bf16(self.mb_obs[t]), t)
-            self.env.step_into(self.mb_actions[t], self.mb_obs[t + 1], self.mb_rewards[t], self.mb_done_u8[t + 1])
+            act = self._sample(self.model.head_bf16(self.mb_obs[t]), t)
+            self.env.step_into(act, self.mb_obs[t + 1], self.mb_rewards[t], self.mb_done_u8[t + 1])
         self.step_counter += T
         dones = self.mb_done_u8.to(torch.float32)
         last_values = self.model.value(self.mb_obs[T]).contiguous()

@@ -194,6 +194,12 @@ int hw_ma_step_host(const HwMaState *state, const void *h_actions, void *d_actio
  * K dimension aligned, the observation has 18 columns. */
 int hw_cast_pad_bf16(const float *src, int cols, void *dst, int dst_cols, int64_t n, void *stream);
 
+/* The same for the two-dimensional diagonal Gaussian policy of the continuous env (DiagGaussianPd): head row = {mean0, mean1, value},
+ * actions[i] = mean + exp(logstd) * N(0, 1) (what the learner stores), env_actions[i] = that clamped to [-1, 1] (what the env acts on). */
+int hw_policy_sample_gaussian2(const void *head, int head_is_bf16, int stride, const float *logstd /* device, 2 floats */, uint64_t seed,
+                               uint64_t env_id0, uint64_t counter, const unsigned long long *counter_offset,
+                               float *actions, float *env_actions, float *neglogp, float *values, int64_t n, void *stream);
+
 /* GAE(gamma, lam) of ppo2's runner (baselines/ppo2/runner.py:53-65) over step-major [T][n] buffers in one launch:
  * dones is uint8 [T + 1][n] (row t: the episode ended before step t; row T: after the last step), last_values [n] the value
  * of the state after the last step.  Writes returns = advantages + values, and the advantages when `advantages` is non-NULL. */

@@ -107,6 +107,36 @@ def test_device_runner_zero_copy_rollout(graphed):
     assert (freq - logp.exp().double().mean(0)).abs().max() < 0.02
 
 
+def test_device_runner_continuous_env():
+    """Gaussian sampler + continuous env: stored transitions are the env's own for the clamped actions, neglogpacs follow
+    DiagGaussianPd, normals have unit variance"""
+    from gym_highway_b200 import HighwayVecEnv
+    from gym_highway_b200.rollout import MlpPolicy, DeviceRunner
+    torch.manual_seed(0)
+    n, T = 4096, 10
+    pol = MlpPolicy(18, continuous=True).cuda()
+    with torch.no_grad():
+        pol.logstd.copy_(torch.tensor([-0.5, -1.0]))
+    run = DeviceRunner(HighwayVecEnv(n, continuous=True, seed=6), pol, nsteps=T, seed=3)
+    run.run_graphed()
+    snapshot = {k: v.clone() for k, v in run.env.state_dict().items()}
+    obs, returns, masks, actions, values, neglogp = [x.clone() for x in run.run_graphed()[:6]]
+    assert actions.shape == (n * T, 2) and actions.dtype == torch.float32 and torch.isfinite(returns).all()
+    o, a = obs.reshape(n, T, 18), actions.reshape(n, T, 2)
+    ref = HighwayVecEnv(n, continuous=True, seed=6)
+    ref.load_state_dict(snapshot)
+    for t in range(T - 1):
+        ob, _, _, _ = ref.step(a[:, t].clamp(-1, 1).contiguous())
+        assert torch.equal(ob, o[:, t + 1, :]), t
+    with torch.no_grad():
+        head = pol.head_bf16(obs).float()
+    std = pol.logstd.detach().exp()
+    z = (actions - head[:, :2]) / std
+    want = 0.5 * (z ** 2).sum(-1) + 0.5 * 1.8378770664093453 * 2 + pol.logstd.detach().sum()
+    assert torch.allclose(neglogp, want, atol=2e-3) and torch.allclose(values, head[:, 2], atol=1e-6)
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02
+
+
 def test_gae_and_cast_kernels_match_torch():
     import ctypes as C
     from gym_highway_b200 import _lib
