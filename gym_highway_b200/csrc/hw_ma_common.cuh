@@ -66,9 +66,10 @@ __device__ __forceinline__ int ob_lane(const MaHead &h, int k) { return (int)((h
 // random operands per constant, scripts/verify_div_by_const.c).
 __device__ __forceinline__ float norm_f64(double raw, const double lo, const double hi)
 {
-    double v = (double)(float)raw;  // np.array(..., dtype=float32)
-    v = (v < lo) ? lo : v;
-    v = (v > hi) ? hi : v;
+    // np.array(..., dtype=float32), then np.clip against bounds that are all exact in float32 (5, 30, 1200, 8, 60, 20): the
+    // clip of the float32 value is the same number in either precision, and two FMNMX are a third of the fp64 compare-selects
+    const float v32 = fminf(fmaxf((float)raw, (float)lo), (float)hi);
+    const double v = (double)v32;
     const double x = dsub(v, lo), c = hi - lo, rc = 1.0 / c;
     const double q0 = dmul(x, rc);
     return (float)__fma_rn(__fma_rn(-q0, c, x), rc, q0);
