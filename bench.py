@@ -92,7 +92,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--envs", type=int, default=0, help="environments PER GPU (weak scaling); 0 = 4,194,304 (SA) / 262,144 (MA)")
-    ap.add_argument("--no-extras", action="store_true", help="skip the configs[1] side measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements of the other BASELINE configs")
     ap.add_argument("--workload", default="sa_discrete")
     ap.add_argument("--agents", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -232,6 +232,73 @@ def ncu_traffic(kind, continuous, n):
         return None
 
 
+def side_measure(kind, continuous, n, dev, rank, args, steps=100, warmup=5, agents=5):
+    """one extra workload timed like the headline (CUDA events per launch, L2 flushed when the working set is small)"""
+    import torch
+    info = dict(kind=kind, continuous=continuous)
+    a = argparse.Namespace(agents=agents)
+    env, A = make_env(info, a, n, dev, rank)
+    acts = make_actions(info, n, A, dev, rank)
+    bps = SA_BYTES_PER_STEP[continuous] if kind == "sa" else ma_bytes_per_step(A, 16)
+    flush = n * bps < 2 * L2_BYTES
+    fb = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if flush else None
+    if kind == "ma":  # no in-kernel random roll-out for the multi-agent env: decorrelate with ordinary steps
+        for w in range(40):
+            env.step_async(acts[w % acts.shape[0]]); env.step_wait()
+    ms, wall = timed_steps(env, acts, steps, warmup, fb, 1, dev)
+    peak = measured_peak()[0]
+    t = float(ms.mean()) * 1e-3
+    out = {"envs": n, "avg_launch_us": t * 1e6, "min_launch_us": float(ms.min()) * 1e3, "env_steps_per_s": n / t,
+           "wall_env_steps_per_s": n * steps / wall, "l2": "flushed between launches" if flush else "working set > L2",
+           "algorithmic_bytes_per_env_step": bps, "achieved_GBps": n * bps / t / 1e9, "roofline_frac": n * bps / t / 1e9 / peak}
+    if kind == "ma":
+        live = float(((env.head[0].view(torch.int32) >> 20) & 31).float().mean().item())
+        b_live = 2 * (36 * A + 16 * live + 40) + 4 * A + 4 * A * (4 * A + 14) + 4 * A + A
+        st = env.episode_statistics()
+        out.update({"agents": A, "agent_steps_per_s": A * n / t, "mean_live_obstacles": live,
+                    "live_slot_bytes_per_env_step": b_live, "roofline_frac_live_slots": n * b_live / t / 1e9 / peak,
+                    "dropped_spawns": st.get("dropped_spawns"), "mean_episode_length": st.get("mean_length")})
+    del env, acts, fb
+    torch.cuda.empty_cache()
+    return out
+
+
+def rollout_measure(dev, rank, world, envs=131072, nsteps=240, rollouts=3):
+    """BASELINE.json configs[3]: ppo2 rollout collection (policy forward + sampling + env step + GAE), DeviceRunner under one
+    CUDA graph per rollout; every rank collects from its own `envs` environments, statistics all-reduced once per rollout"""
+    import torch
+    import torch.distributed as dist
+    from gym_highway_b200 import HighwayVecEnv
+    from gym_highway_b200.rollout import DeviceRunner, MlpPolicy
+    torch.manual_seed(0)
+    env = HighwayVecEnv(envs, seed=0, device=dev, env_id0=rank * envs)
+    pol = MlpPolicy(18, 4, bf16_inference=True).to(dev)
+    run = DeviceRunner(env, pol, nsteps=nsteps, gamma=0.99, lam=0.95, seed=0)
+    run.run_graphed()  # eager warm-up rollout, capture, first replay
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(rollouts):
+        run.run_graphed()
+        stats = env.episode_statistics(reset=True)  # one all_reduce of 8 counters per rollout
+    t1.record()
+    torch.cuda.synchronize(dev)
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    out = {"workload": "configs[3]: ppo2 rollout collection, %d envs/GPU x %d GPU(s), T=%d, MLP 18-256-256-256 (bf16 GEMMs) on device, "
+                       "fused sampling kernel, env step_into, hw_gae, one CUDA graph per rollout" % (envs, world, nsteps),
+           "rollout_env_steps_per_s": world * envs * nsteps * rollouts / (ms * 1e-3), "ms_per_rollout": ms / rollouts,
+           "us_per_step": 1e3 * ms / rollouts / nsteps, "episodes_last_rollout": stats["episodes"]}
+    del run, env, pol
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     if args.envs <= 0:
@@ -247,6 +314,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from gym_highway_b200 import numa
+    numa_note = numa.bind_to_gpu(local_rank)  # before the first pinned allocation: host buffers land on the GPU's NUMA node
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -264,9 +333,9 @@ def main():
     clocks = sampler.result()
     total_ms = float(dev_ms.sum())
     if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, t_wall], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        total_ms, t_wall = float(t[0].item()), float(t[1].item())
     value = world * n * args.steps / (total_ms * 1e-3)
 
     # end to end through the host-buffer C-ABI call: pinned host actions in, host obs/rew/done out
@@ -288,11 +357,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     act_bytes = int(h_acts[0].nbytes)
-    out_bytes = n * A * (4 * A + 14 if info["kind"] == "ma" else 18) * 4 + n * A * 4 + n * A
+    out_bytes = int(getattr(env, "host_d2h_bytes_per_step", n * A * (4 * A + 14 if info["kind"] == "ma" else 18) * 4 + n * A * 4 + n * A))
     e2e = {"value": world * n * e2e_steps / t_e2e, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
            "d2h_bytes_per_step": out_bytes, "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps,
            "api": ("HighwayVecEnv.step_host -> hw_sa_step_host" if info["kind"] == "sa" else "HighwayMAVecEnv.step_host -> hw_ma_step_host")
-                  + " (C ABI, host buffers: pinned-host actions H2D, kernel, obs/rew/done D2H, stream drain, all inside the call)"}
+                  + " (C ABI, host buffers: pinned-host actions H2D, kernel, obs/rew/done D2H, stream drain, all inside the call)",
+           "host_binding": numa_note}
     stats = env.episode_statistics()
     live = None
     if info["kind"] == "ma":
@@ -300,17 +370,23 @@ def main():
     del env, acts
     torch.cuda.empty_cache()
 
-    # BASELINE.json configs[1]: 65,536 single-agent envs on one GPU (0.7 waves: latency-bound), L2 flushed between launches
-    configs1 = None
-    if info["kind"] == "sa" and rank == 0 and n != 65536 and not args.no_extras:
-        fb = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-        e1, _ = make_env(info, args, 65536, dev, rank)
-        a1 = make_actions(info, 65536, 1, dev, rank)
-        ms1, _ = timed_steps(e1, a1, 200, 10, fb, 1, dev)
-        configs1 = {"workload": "configs[1]: 65,536 envs on 1 GPU, L2 flushed between launches", "env_steps_per_s": 65536 / (float(ms1.mean()) * 1e-3),
-                    "avg_launch_us": float(ms1.mean()) * 1e3, "roofline_frac": 65536 * info["bytes_per_step"] / (float(ms1.mean()) * 1e-3) / 1e9 / measured_peak()[0]}
-        del e1, a1, fb
-        torch.cuda.empty_cache()
+    # side measurements of the other BASELINE.json configs (one GPU; the driver's N=1 run records them)
+    extras = {}
+    if not args.no_extras and world == 1 and info["kind"] == "sa" and not info["continuous"] and n != 65536:
+        # configs[1]: 65,536 single-agent envs on one GPU (0.43 waves: latency-bound), L2 flushed between launches
+        c1 = side_measure("sa", False, 65536, dev, rank, args, steps=200, warmup=10)
+        extras["configs1"] = dict(c1, workload="configs[1]: 65,536 single-agent envs on 1 GPU, discrete random actions")
+        extras["sa_16m"] = dict(side_measure("sa", False, 16777216, dev, rank, args, steps=30, warmup=3),
+                                workload="configs[4]: the 16,777,216-env point (largest single-GPU configuration), discrete")
+        extras["continuous"] = dict(side_measure("sa", True, 4194304, dev, rank, args, steps=60, warmup=5),
+                                    workload="single-agent continuous actions (HighwayEnvContinuous), 4,194,304 envs")
+        extras["configs2"] = {
+            "workload": "configs[2]: multi-agent env, 5 cars (+3..16 obstacles) per env, uniform random discrete actions, car-car collisions",
+            "envs_16384": side_measure("ma", False, 16384, dev, rank, args, steps=200, warmup=10),
+            "envs_262144": side_measure("ma", False, 262144, dev, rank, args, steps=60, warmup=5),
+            "continuous_262144": side_measure("ma", True, 262144, dev, rank, args, steps=60, warmup=5)}
+    if not args.no_extras and info["kind"] == "sa" and not info["continuous"]:
+        extras["configs3"] = rollout_measure(dev, rank, world)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -324,8 +400,11 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": info["dtype"], "data": "synthetic",
             "config": {"workload": info["name"], "envs_per_gpu": n, "ticks_per_step": 9,
+                       "steering": "fast (vx*tan/4, one rounding: discrete state bit-exact, floats within 1e-5 relative per step; "
+                                   "HW_FLAG_EXACT_STEERING, the bit-exact mode of the golden tests, costs ~20 %)",
                        "baseline_config": ("BASELINE.json configs[4] (scaling sweep 4k-16M envs, HBM GB/s vs roofline): the %d-env point, weak-scaled over the GPUs; "
-                                           "configs[1] (65,536 envs on one GPU, launch/latency-bound) is measured in the same run and reported under \"configs1\"" % n)
+                                           "configs[1] (65,536 envs, launch/latency-bound), the 16M point, continuous actions, configs[2] (multi-agent) and "
+                                           "configs[3] (ppo2 rollout) are measured in the same run and reported under their own keys" % n)
                                           if info["kind"] == "sa" else "BASELINE.json configs[2]/[4]: multi-agent env, %d-env point" % n,
                        "l2": "flushed between timed launches (256 MiB overwrite outside the event pairs)" if flush
                              else "inputs larger than L2 (%.0f MB per launch vs 126 MB), no flush" % (working_set / 1e6),
@@ -336,10 +415,9 @@ def main():
                          "algorithmic_bytes_per_env_step": bps,
                          "avg_launch_us": avg_launch_s * 1e6, "min_launch_us": float(dev_ms.min()) * 1e3},
             "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,
-            "wall_ms_per_step": 1e3 * t_wall / args.steps, "episodes": stats,
+            "wall_ms_per_step": 1e3 * t_wall / args.steps, "value_wall": world * n * args.steps / t_wall, "episodes": stats,
         }
-        if configs1:
-            line["configs1"] = configs1
+        line.update(extras)
         if info["kind"] == "ma":
             line["agent_steps_per_s"] = value * A
             line["mean_live_obstacles"] = live

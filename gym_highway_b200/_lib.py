@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhighway_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FLAG_CONTINUOUS = 1
 FLAG_NO_INF_OBS = 2
@@ -76,7 +76,7 @@ _EXPORTS = {
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hw_sa_step_host": (C.c_int, [C.POINTER(HwSaState), C.c_void_p, C.c_void_p, C.POINTER(HwSaOut),
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HwSimParams),
-                                  C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
+                                  C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

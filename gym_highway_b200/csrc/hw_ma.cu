@@ -343,7 +343,8 @@ __device__ __forceinline__ void ma_step_env(const MaPtrs &S, double *sm_car, dou
     double r[kMaxA];
 #pragma unroll
     for (int a = 0; a < kMaxA; ++a) r[a] = 0.0;
-    uint32_t done = 0;
+    uint32_t done = (h.flags >> 8) & 31u;  // is_done persists until reset() (highway_core.py:239, :420)
+    h.flags &= 0xFFu;
     for (int t = 0; t < C.ticks_per_step; ++t) {
         ma_tick<CONT, EXACT>(h, sm_car, sm_ob, cbits, A, K, C, inf_obs, act_d, act_c, seed, env_id0 + (uint64_t)i, r, done);
         if (done) break;  // highway_env.py:85-86
@@ -377,6 +378,7 @@ __device__ __forceinline__ void ma_step_env(const MaPtrs &S, double *sm_car, dou
             h.flags = keep;  // sticky diagnostics survive the reset
         }
     }
+    if (!(done && autoreset)) h.flags |= done << 8;
     ma_observe(h, sm_car, sm_ob, A, obs + i * (int64_t)A * D);
     ma_store(h, sm_car, sm_ob, cbits, S, i, n);
 }

@@ -31,7 +31,8 @@ struct MaHead {
     uint32_t newest[3];  // slot index, 31 = retired
     uint32_t olane;      // 2 bits per slot
     uint32_t ofresh;     // bit k: slot k still carries pygame's default rect (0,0,76,38)
-    uint32_t flags;      // bit 0: a spawn was dropped for lack of slots, bit 1: a lane had no obstacle to observe
+    uint32_t flags;      // bit 0: a spawn was dropped for lack of slots, bit 1: a lane had no obstacle to observe;
+                         // in memory bits 8..12 hold the per-car done flags that persist until reset (no auto-reset only)
     uint32_t nc_obs, nc_agent, spawn_ctr, ep_len;
     double ep_ret;
 };
@@ -57,6 +58,9 @@ __device__ __forceinline__ void ma_store_head(const MaHead &h, const MaPtrs &S, 
     S.head[4 * n + i] = h.nc_obs; S.head[5 * n + i] = h.nc_agent; S.head[6 * n + i] = h.spawn_ctr; S.head[7 * n + i] = h.ep_len;
     S.head[8 * n + i] = (uint32_t)__double2loint(h.ep_ret); S.head[9 * n + i] = (uint32_t)__double2hiint(h.ep_ret);
 }
+
+// 2-bit lane fields of the live slots; nobs == 16 would be a shift by 32 (undefined in C++)
+__device__ __forceinline__ uint32_t live_mask(uint32_t nobs) { return nobs >= 16u ? 0xFFFFFFFFu : (1u << (2 * nobs)) - 1u; }
 
 __device__ __forceinline__ int ob_lane(const MaHead &h, int k) { return (int)((h.olane >> (2 * k)) & 3u); }
 

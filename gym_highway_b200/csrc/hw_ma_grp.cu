@@ -195,7 +195,7 @@ struct GrpStep {
         }
         // only the slots that drive in this lane (usually one): 2-bit lane fields of `olane` equal to `lane`, in slot order
         const uint32_t diff = h.olane ^ ((uint32_t)lane * 0x55555555u);
-        uint32_t same = ~(diff | (diff >> 1)) & 0x55555555u & ((1u << (2 * h.nobs)) - 1u);
+        uint32_t same = ~(diff | (diff >> 1)) & 0x55555555u & live_mask(h.nobs);
         while (same) {
             const int k = (__ffs((int)same) - 1) >> 1;
             same &= same - 1u;
@@ -418,7 +418,7 @@ struct GrpStep {
         }
         // per lane the obstacle nearest in raw x (first wins ties, insertion order): slot A-1+lane.  The slots of a lane are
         // picked out of the 2-bit lane fields of `olane`, so each slot is visited once, by its own lane's search.
-        const uint32_t live = (1u << (2 * h.nobs)) - 1u;
+        const uint32_t live = live_mask(h.nobs);
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             const int s = A - 1 + l;
@@ -446,6 +446,9 @@ struct GrpStep {
     __device__ __forceinline__ void load(const MaPtrs &S, const int64_t i, const int64_t n)
     {
         ma_load_head(h, S, i, n);
+        // is_done persists until reset() (highway_core.py:239, :420): with HW_FLAG_NO_AUTORESET a car that finished in an
+        // earlier step is still done, and the step then ends after its first tick (highway_env.py:85-86)
+        done = (h.flags >> 8) & 31u; h.flags &= 0xFFu;
         c.px = c.py = c.rx = c.vx = c.vy = c.acc = c.steer = c.cruise = 0.0; c.b = 0;
         if (g < A) {
             const float *p = S.cars + (int64_t)(g * 9) * n + i;
@@ -604,6 +607,7 @@ ma_grp_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
     if (live) {
         if (is_car) st.observe(obs + (i * A + g) * (int64_t)D);
         // a lane without an obstacle to observe is the same finding for every car; the header is stored by lane 0 (always a car)
+        if (!(st.done && autoreset)) st.h.flags |= st.done << 8;
         st.store(S, i, n);
     }
     if (stats) {

@@ -551,6 +551,10 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                 if (autoreset) {
                     sa_reset_env(e);
                     was_reset = true; ncoll_step = 0; ret_milli_step = 0; len_step = 0;
+                } else if (tick >= 0xFF00u) {
+                    // gym per-env semantics (no auto-reset) stepped far past the time-out: the 16-bit tick field saturates
+                    // instead of carrying into the lane bits (the episode has been over for 60000 ticks; only `done` matters)
+                    e.bits = (e.bits & ~HW_BITS_TICK_MASK) | 0xFF00u;
                 }
             }
         }
@@ -734,25 +738,24 @@ int hw_sa_observe(const HwSaState *state, float *obs, int64_t n, void *stream)
 
 int hw_sa_step_host(const HwSaState *state, const void *h_actions, void *d_actions, const HwSaOut *d_out,
                     float *h_obs, float *h_rew, uint8_t *h_done, const HwSimParams *params,
-                    uint64_t seed, uint64_t env_id0, int64_t n, int flags, void *stream)
+                    uint64_t seed, uint64_t env_id0, int64_t n, int flags, void *stream, void *aux_stream)
 {
     if (!h_actions || !d_actions || !d_out || !h_obs || !h_rew || !h_done || n <= 0) return HW_E_BADARG;
-    cudaStream_t s = (cudaStream_t)stream;
+    cudaStream_t s = (cudaStream_t)stream, s2 = (cudaStream_t)aux_stream;
     const size_t asize = (flags & HW_FLAG_CONTINUOUS) ? 2 * sizeof(float) : sizeof(int32_t);
     // The call is bound by the device-to-host copy of the observations (72 of the 81 bytes per environment that cross PCIe).
-    // Large batches are therefore cut into chunks that alternate between the caller's stream and a second one, so that
-    // the action upload and the kernel of chunk c+1 run under the download of chunk c.
+    // Large batches are therefore cut into two halves that alternate between the caller's stream and the caller's auxiliary
+    // stream (both live as long as the environment: nothing is created per call but one untimed event), so that the action
+    // upload and the kernel of the second half run under the download of the first.
     // (Measured on B200 / PCIe Gen5 at 4 M envs: 6.87 ms unsplit, 6.73 ms in two halves, worse again from eight chunks on:
     // the download alone is 6.3 ms at the link's ~51 GB/s, so there is little left to hide.)
-    const int chunks = (n >= 262144) ? 2 : 1;
+    const int chunks = (n >= 262144 && s2 != nullptr && s2 != s) ? 2 : 1;
     const int64_t per = (((n + chunks - 1) / chunks) + 127) & ~(int64_t)127;
-    cudaStream_t s2 = nullptr;
     cudaEvent_t ev = nullptr;
     cudaError_t ce = cudaSuccess;
     if (chunks > 1) {
-        if ((ce = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)) != cudaSuccess) return (int)ce;
-        if ((ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) { cudaStreamDestroy(s2); return (int)ce; }
-        cudaEventRecord(ev, s);           // the second stream starts after whatever the caller has queued
+        if ((ce = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return (int)ce;
+        cudaEventRecord(ev, s);           // the auxiliary stream starts after whatever the caller has queued
         cudaStreamWaitEvent(s2, ev, 0);
     }
     int rc = 0;
@@ -770,11 +773,11 @@ int hw_sa_step_host(const HwSaState *state, const void *h_actions, void *d_actio
         if (ce != cudaSuccess) rc = (int)ce;
     }
     if (chunks > 1) {
-        cudaEventRecord(ev, s2);          // and the caller's stream ends after the second one
+        cudaEventRecord(ev, s2);          // and the caller's stream ends after the auxiliary one
         cudaStreamWaitEvent(s, ev, 0);
+        cudaEventDestroy(ev);             // released once the recorded work has completed; the stream wait above is already queued
     }
     ce = cudaStreamSynchronize(s);
-    if (chunks > 1) { cudaEventDestroy(ev); cudaStreamDestroy(s2); }
     return rc ? rc : (int)ce;
 }
 

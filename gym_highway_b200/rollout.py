@@ -34,29 +34,49 @@ class MlpPolicy(nn.Module):
         h = self.body(obs)
         return self.pi(h), self.vf(h).squeeze(-1)
 
+    def _alloc_bf16(self):
+        """persistent bf16 weight buffers, allocated ONCE per device: [in, out] layouts, the input width (18) and the merged
+        head width (n_out + 1) zero-padded to multiples of 8 so that cuBLASLt picks its aligned tensor-core kernels (the
+        unaligned fallbacks are 3x slower at 10^5 rows).  The tensors are never rebound afterwards - a CUDA graph that
+        captured a rollout holds their addresses."""
+        lin = [m for m in self.body if isinstance(m, nn.Linear)]
+        dev = lin[0].weight.device
+        body = []
+        for k, m in enumerate(lin):
+            kin = m.in_features + ((-m.in_features) % 8 if k == 0 else 0)
+            body.append((torch.zeros(kin, m.out_features, dtype=torch.bfloat16, device=dev),
+                         torch.zeros(m.out_features, dtype=torch.bfloat16, device=dev)))
+        self._n_head = self.pi.out_features + 1
+        hp = self._n_head + (-self._n_head) % 8
+        self._bf16_body = body
+        self._bf16_head_w = torch.zeros(self.pi.in_features, hp, dtype=torch.bfloat16, device=dev)
+        self._bf16_head_b = torch.zeros(hp, dtype=torch.bfloat16, device=dev)
+        self._bf16_dev = dev
+        self._bf16_ver = None
+
+    @torch.no_grad()
+    def refresh_bf16_(self):
+        """re-cast the fp32 parameters into the persistent bf16 buffers IN PLACE (a handful of small copy kernels).  The
+        rollout runners call this at the top of every run(), so the casts are part of a captured CUDA graph and a replay
+        after optimizer.step() samples from the updated policy."""
+        lin = [m for m in self.body if isinstance(m, nn.Linear)]
+        if getattr(self, "_bf16_body", None) is None or self._bf16_dev != lin[0].weight.device:
+            self._alloc_bf16()
+        for (w, b), m in zip(self._bf16_body, lin):
+            w[:m.in_features].copy_(m.weight.t())
+            b.copy_(m.bias)
+        n = self.pi.out_features
+        self._bf16_head_w[:, :n].copy_(self.pi.weight.t())
+        self._bf16_head_w[:, n:n + 1].copy_(self.vf.weight.t())
+        self._bf16_head_b[:n].copy_(self.pi.bias)
+        self._bf16_head_b[n:n + 1].copy_(self.vf.bias)
+        self._bf16_ver = tuple(p._version for p in self.parameters())
+
     def _bf16_weights(self):
-        """bf16 copies of the weights for rollout-time inference, rebuilt when a parameter has been updated in place.
-        The input width (18) and the merged head width (n_out + 1) are zero-padded to multiples of 8 so that cuBLASLt
-        picks its aligned tensor-core kernels (the unaligned fallbacks are 3x slower at 10^5 rows)."""
-        ver = tuple(p._version for p in self.parameters())
-        if getattr(self, "_bf16_ver", None) != ver:
-            lin = [m for m in self.body if isinstance(m, nn.Linear)]
-            body = []
-            for k, m in enumerate(lin):
-                w = m.weight.detach().to(torch.bfloat16).t().contiguous()  # [in, out]
-                if k == 0 and w.shape[0] % 8:
-                    w = torch.cat([w, w.new_zeros(8 - w.shape[0] % 8, w.shape[1])], 0).contiguous()
-                body.append((w, m.bias.detach().to(torch.bfloat16)))
-            self._bf16_body = body
-            hw = torch.cat([self.pi.weight, self.vf.weight], 0).detach().to(torch.bfloat16)   # [n_out + 1, hidden]
-            hb = torch.cat([self.pi.bias, self.vf.bias], 0).detach().to(torch.bfloat16)
-            self._n_head = hw.shape[0]
-            if hw.shape[0] % 8:
-                pad = 8 - hw.shape[0] % 8
-                hw = torch.cat([hw, hw.new_zeros(pad, hw.shape[1])], 0)
-                hb = torch.cat([hb, hb.new_zeros(pad)], 0)
-            self._bf16_head_w, self._bf16_head_b = hw.t().contiguous(), hb
-            self._bf16_ver = ver
+        """the persistent bf16 copies, refreshed in place when a parameter has been updated since the last refresh (eager
+        use; under graph capture / replay the runners refresh explicitly, the version check is host-side state)"""
+        if getattr(self, "_bf16_body", None) is None or self._bf16_ver != tuple(p._version for p in self.parameters()):
+            self.refresh_bf16_()
         return self._bf16_body, self._bf16_head_w, self._bf16_head_b
 
     def _forward_bf16(self, obs):
@@ -106,7 +126,7 @@ class MlpPolicy(nn.Module):
             std = self.logstd.exp()
             a = out + std * torch.randn(out.shape, device=out.device, generator=generator)
             neglogp = (0.5 * (((a - out) / std) ** 2).sum(-1) + 0.5 * 1.8378770664093453 * a.shape[-1] + self.logstd.sum())
-            return a.clamp(-1, 1), v, neglogp
+            return a, v, neglogp  # the raw sample: what the learner stores and what neglogp belongs to (clamp only the env's copy)
         logp = torch.log_softmax(out, dim=-1)
         # categorical sample by inverse CDF on one uniform per env (cheaper than torch.multinomial at 10^5..10^6 rows)
         # (running sums over the handful of actions are spelled out: torch.cumsum over a last dimension of 4 costs 0.7 ms at 131k rows)
@@ -182,14 +202,17 @@ class Runner(object):
     @torch.no_grad()
     def run(self, want_epinfos=True):
         epinfos = []
+        if getattr(self.model, "bf16_inference", False):
+            self.model.refresh_bf16_()  # in place, inside a captured graph too: replays follow optimizer.step()
+        cont = getattr(self.env, "continuous", False)
         for t in range(self.nsteps):
             actions, values, neglogpacs = self.model.step(self.obs, generator=self.generator)
             self.mb_obs[t].copy_(self.obs)
-            self.mb_actions[t].copy_(actions)
+            self.mb_actions[t].copy_(actions)   # the raw sample (what neglogpacs belongs to) ...
             self.mb_values[t].copy_(values)
             self.mb_neglogpacs[t].copy_(neglogpacs)
             self.mb_dones[t].copy_(self.dones)
-            obs, rewards, dones, infos = self.env.step(actions)
+            obs, rewards, dones, infos = self.env.step(actions.clamp(-1, 1) if cont else actions)  # ... the env acts on it clamped to its Box
             self.obs = obs
             self.dones = dones.to(torch.float32)
             self.mb_rewards[t].copy_(rewards)
@@ -251,13 +274,16 @@ class A2CRunner(object):
 
     @torch.no_grad()
     def run(self):
+        if getattr(self.model, "bf16_inference", False):
+            self.model.refresh_bf16_()
+        cont = getattr(self.env, "continuous", False)
         for t in range(self.nsteps):
             actions, values, _ = self.model.step(self.obs, generator=self.generator)
             self.mb_obs[t].copy_(self.obs)
             self.mb_actions[t].copy_(actions)
             self.mb_values[t].copy_(values)
             self.mb_dones[t].copy_(self.dones)
-            obs, rewards, dones, _ = self.env.step(actions)
+            obs, rewards, dones, _ = self.env.step(actions.clamp(-1, 1) if cont else actions)
             self.obs = obs
             self.dones = dones.to(torch.float32)
             self.mb_rewards[t].copy_(rewards)
@@ -321,6 +347,7 @@ class DeviceRunner(object):
     @torch.no_grad()
     def run(self):
         T = self.nsteps
+        self.model.refresh_bf16_()  # bf16 weight copies re-cast in place: part of the captured graph, so replays see optimizer steps
         # the last observation / done row of the previous rollout is the first of this one
         self.mb_obs[0].copy_(self.mb_obs[T])
         self.mb_done_u8[0].copy_(self.mb_done_u8[T])

@@ -185,6 +185,7 @@ class HighwayVecEnv(VecEnv):
                                     o['term'].data_ptr(), self.stats.data_ptr() if track_stats else 0)
                        for o in self._out]
         self._cur = 0
+        self._serial = 0  # launches that changed the state so far (lazy infos check it)
         self._pending = None
         self._actions_keepalive = None
         self._run_time = _run_time_table(self.params)
@@ -234,6 +235,7 @@ class HighwayVecEnv(VecEnv):
         """reset every environment; returns obs [N, 18] float32"""
         assert not self.closed
         self._pending = None
+        self._serial += 1
         out = self._out[self._cur]
         with torch.cuda.device(self.device):
             rc = self._lib.hw_sa_reset(C.byref(self._state_c), None, _as_ptr(out['obs']), self.num_envs, self._stream())
@@ -263,6 +265,7 @@ class HighwayVecEnv(VecEnv):
             raise AlreadySteppingError()
         a = self._coerce_actions(actions)
         self._cur ^= 1
+        self._serial += 1
         with torch.cuda.device(self.device):
             rc = self._lib.hw_sa_step(C.byref(self._state_c), _as_ptr(a), C.byref(self._out_c[self._cur]),
                                       C.byref(self.params), self._seed, self._env_id0, self.num_envs, self._flags,
@@ -285,6 +288,7 @@ class HighwayVecEnv(VecEnv):
         [T, N] buffers - instead of the env's own double-buffered outputs.  `actions` must already be an int32 [N]
         (float32 [N, 2] when continuous) tensor on this device.  Asynchronous; no infos (use episode_statistics())."""
         assert not self.closed and self._pending is None
+        self._serial += 1
         out = _lib.HwSaOut(obs.data_ptr(), rew.data_ptr(), done.data_ptr(), self._out[0]['term'].data_ptr(),
                            self.stats.data_ptr() if self.stats is not None else 0)
         with torch.cuda.device(self.device):
@@ -296,6 +300,7 @@ class HighwayVecEnv(VecEnv):
         """`steps` env.steps with in-kernel uniform random actions in one launch (benchmark / warm-up);
         returns the last step's (obs, rew, done)"""
         self._cur ^= 1
+        self._serial += 1
         with torch.cuda.device(self.device):
             rc = self._lib.hw_sa_rollout_random(C.byref(self._state_c), C.byref(self._out_c[self._cur]),
                                                 C.byref(self.params), self._seed, self._env_id0, int(action_ctr0),
@@ -316,21 +321,31 @@ class HighwayVecEnv(VecEnv):
                 rew=torch.empty(n, dtype=torch.float32).pin_memory(),
                 done=torch.empty(n, dtype=torch.uint8).pin_memory(),
                 d_act=torch.empty((n, 2) if self.continuous else (n,),
-                                  dtype=torch.float32 if self.continuous else torch.int32, device=self.device))
+                                  dtype=torch.float32 if self.continuous else torch.int32, device=self.device),
+                aux=torch.cuda.Stream(device=self.device))  # second stream of the two-half pipeline, lives with the env
         h = self._host
         h['act'].copy_(torch.as_tensor(np.asarray(actions)).reshape(h['act'].shape))
         self._cur ^= 1
+        self._serial += 1
         with torch.cuda.device(self.device):
             rc = self._lib.hw_sa_step_host(C.byref(self._state_c), _as_ptr(h['act']), _as_ptr(h['d_act']),
                                            C.byref(self._out_c[self._cur]), _as_ptr(h['obs']), _as_ptr(h['rew']),
                                            _as_ptr(h['done']), C.byref(self.params), self._seed, self._env_id0,
-                                           n, self._flags, self._stream())
+                                           n, self._flags, self._stream(), C.c_void_p(h['aux'].cuda_stream))
         _lib.check(rc, "hw_sa_step_host")
         return h['obs'].numpy(), h['rew'].numpy(), h['done'].numpy().view(np.bool_)  # the kernel writes 0 / 1
 
     # ------------------------------------------------------------------ infos / statistics
     def _make_info_fetcher(self, out):
+        serial = self._serial
+        rt = lambda tick: float(self._run_time[min(int(tick), len(self._run_time) - 1)])
+
         def fetch(episodes_only):
+            # terminal rows come from this step's own (double-buffered) outputs; the non-terminal rows are read from the
+            # live state, so they are only this step's while no later step has been launched
+            if self._serial - serial > (1 if episodes_only else 0):
+                raise RuntimeError("the infos of a step must be read before the %s step() (they are built lazily from "
+                                   "device tensors that a later step overwrites)" % ("second following" if episodes_only else "next"))
             done = out['done'].cpu().numpy().astype(bool)
             term = out['term'].cpu().numpy()
             now = round(time.time() - self.tstart, 6)
@@ -342,11 +357,11 @@ class HighwayVecEnv(VecEnv):
             infos = []
             for i in range(self.num_envs):
                 if done[i]:
-                    info = {"run_time": float(self._run_time[term[i, 0]]), "num_obs_collisions": int(term[i, 1]),
+                    info = {"run_time": rt(term[i, 0]), "num_obs_collisions": int(term[i, 1]),
                             "num_agent_collisions": 0,
                             "episode": {"r": round(term[i, 2] / 1000.0, 6), "l": int(term[i, 3]), "t": now}}
                 else:
-                    info = {"run_time": float(self._run_time[tick[i]]), "num_obs_collisions": int(stat[i, 0]),
+                    info = {"run_time": rt(tick[i]), "num_obs_collisions": int(stat[i, 0]),
                             "num_agent_collisions": 0}
                 infos.append(info)
             return infos

@@ -76,6 +76,7 @@ class HighwayMAVecEnv(VecEnv):
         self._out_c = [_lib.HwMaOut(o['obs'].data_ptr(), o['rew'].data_ptr(), o['done'].data_ptr(), o['term'].data_ptr(),
                                     self.stats.data_ptr() if track_stats else 0) for o in self._out]
         self._cur = 0
+        self._serial = 0
         self._pending = None
         self._keep = None
         self._run_time = _run_time_table(self.params)
@@ -116,6 +117,7 @@ class HighwayMAVecEnv(VecEnv):
     def reset(self):
         assert not self.closed
         self._pending = None
+        self._serial += 1
         out = self._out[self._cur]
         with torch.cuda.device(self.device):
             rc = self._lib.hw_ma_reset(C.byref(self._state_c), None, _as_ptr(out['obs']), self.num_envs, self._stream())
@@ -135,6 +137,7 @@ class HighwayMAVecEnv(VecEnv):
             raise AlreadySteppingError()
         a = self._coerce_actions(actions)
         self._cur ^= 1
+        self._serial += 1
         with torch.cuda.device(self.device):
             rc = self._lib.hw_ma_step(C.byref(self._state_c), _as_ptr(a), C.byref(self._out_c[self._cur]),
                                       C.byref(self.params), self._seed, self._env_id0, self.num_envs, self._flags,
@@ -163,6 +166,7 @@ class HighwayMAVecEnv(VecEnv):
         h = self._host
         h['act'].copy_(torch.as_tensor(np.asarray(actions)).reshape(h['act'].shape))
         self._cur ^= 1
+        self._serial += 1
         with torch.cuda.device(self.device):
             rc = self._lib.hw_ma_step_host(C.byref(self._state_c), _as_ptr(h['act']), _as_ptr(h['d_act']),
                                            C.byref(self._out_c[self._cur]), _as_ptr(h['obs']), _as_ptr(h['rew']),
@@ -172,7 +176,13 @@ class HighwayMAVecEnv(VecEnv):
         return h['obs'].numpy(), h['rew'].numpy(), h['done'].numpy().view(np.bool_)
 
     def _make_info_fetcher(self, out):
+        serial = self._serial
+        rtab = lambda tick: float(self._run_time[min(int(tick), len(self._run_time) - 1)])
+
         def fetch(episodes_only):
+            if self._serial - serial > (1 if episodes_only else 0):
+                raise RuntimeError("the infos of a step must be read before the %s step() (they are built lazily from "
+                                   "device tensors that a later step overwrites)" % ("second following" if episodes_only else "next"))
             done = out['done'].cpu().numpy().astype(bool)
             any_done = done.any(axis=1)
             term = out['term'].cpu().numpy()
@@ -184,9 +194,9 @@ class HighwayMAVecEnv(VecEnv):
             infos = []
             for i in range(self.num_envs):
                 if any_done[i]:
-                    rt, nco, nca = float(self._run_time[int(term[i, 0])]), int(term[i, 1]), int(term[i, 2])
+                    rt, nco, nca = rtab(term[i, 0]), int(term[i, 1]), int(term[i, 2])
                 else:
-                    rt, nco, nca = float(self._run_time[int(head[0, i] & 0xFFFF)]), int(head[4, i]), int(head[5, i])
+                    rt, nco, nca = rtab(head[0, i] & 0xFFFF), int(head[4, i]), int(head[5, i])
                 info = {'n': [{"rewards": float(rew[i, a]), "run_time": rt, "num_obs_collisions": nco,
                                "num_agent_collisions": nca} for a in range(self.num_agents)]}
                 if any_done[i]:
@@ -211,7 +221,7 @@ class HighwayMAVecEnv(VecEnv):
 
     def diagnostics(self):
         """sticky per-env flags: bit 0 = a spawn was dropped (all slots live), bit 1 = a lane had no obstacle to observe"""
-        return (self.head[3].view(torch.int32) >> 16) & 0xFFFF
+        return (self.head[3].view(torch.int32) >> 16) & 0xFF  # bits 24..28 of the word hold the persistent per-car done flags
 
     def state_dict(self):
         return dict(cars=self.cars.clone(), obst=self.obst.clone(), head=self.head.clone())

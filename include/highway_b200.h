@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define HW_ABI_VERSION 1
+#define HW_ABI_VERSION 2
 
 #define HW_E_BADARG (-1)   /* null pointer / non-positive size / unsupported combination */
 #define HW_E_ALIGN  (-2)   /* a 16-byte-aligned pointer was required */
@@ -124,12 +124,14 @@ int hw_sa_rollout_random(const HwSaState *state, const HwSaOut *out, const HwSim
                          int64_t n, int flags, void *stream);
 
 /* Host-buffer step: HOST actions -> device -> step -> HOST obs/rew/done, all on `stream`, returns
- * after the copies have landed.  Batches of 262,144 environments and more run as two half-batch launches, the second on
- * a stream created for the duration of the call, so that its upload and kernel overlap the first half's download.  d_actions and d_out are caller-owned DEVICE staging buffers of the
- * same shapes; h_* should be page-locked for full copy bandwidth. */
+ * after the copies have landed.  When `aux_stream` is a second (caller-owned, long-lived) stream, batches of
+ * 262,144 environments and more run as two half-batch launches, the second one on `aux_stream`, so that its upload
+ * and kernel overlap the first half's download; with aux_stream NULL the call is one upload, one launch, one download.
+ * d_actions and d_out are caller-owned DEVICE staging buffers of the same shapes; h_* should be page-locked
+ * (and allocated on the GPU's NUMA node) for full copy bandwidth. */
 int hw_sa_step_host(const HwSaState *state, const void *h_actions, void *d_actions, const HwSaOut *d_out,
                     float *h_obs, float *h_rew, uint8_t *h_done, const HwSimParams *params,
-                    uint64_t seed, uint64_t env_id0, int64_t n, int flags, void *stream);
+                    uint64_t seed, uint64_t env_id0, int64_t n, int flags, void *stream, void *aux_stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-agent environments: A cars (1..5) and up to K live obstacles (3..16) per environment.
@@ -145,6 +147,8 @@ int hw_sa_step_host(const HwSaState *state, const void *h_actions, void *d_actio
  *        2  lane id of slot k in bits 2k..2k+1
  *        3  bit k: slot k still has pygame's default rect (spawned, not yet updated)
  *           bit 16: a spawn was dropped because all K slots were live; bit 17: a lane had no obstacle to observe
+ *           bits 24..28: car a is done since an earlier step (is_done persists until reset, highway_core.py:239,:420;
+ *           only ever non-zero with HW_FLAG_NO_AUTORESET)
  *        4  n_obs_collisions  5  n_agent_collisions  6  spawn_ctr  7  episode_len
  *        8,9  episode return (sum of every car's reward), IEEE double, low word first
  */

@@ -302,7 +302,7 @@ static inline double q32(double v) { return (double)(float)v; }
 typedef struct {
     int n, A, K;
     double *car; int32_t *lane, *cflags, *tick, *leader, *nobs; double *obst; int32_t *olane, *ofresh, *newest;
-    int32_t *nc_obs, *nc_agent; uint32_t *spawn_ctr; double *ep_ret; int32_t *ep_len, *overflow;
+    int32_t *nc_obs, *nc_agent; uint32_t *spawn_ctr; double *ep_ret; int32_t *ep_len, *overflow, *done_mask;
     const int32_t *act_d; const double *act_c;
     float *obs; double *rew; uint8_t *done; double *term;
     double dt; int ticks_per_step, timeout_tick; uint64_t seed, env_id0; int hwflags;
@@ -360,7 +360,8 @@ static void *ma_step_range(void *arg)
         ma_env e;
         ma_unpack(J, i, &e);
         double r[MA_MAX_A]; uint8_t d[MA_MAX_A]; int used = 0;
-        for (int a = 0; a < A; ++a) { r[a] = 0.0; d[a] = 0; }
+        /* is_done persists until reset() (highway_core.py:239, :420): a car that finished in an earlier step is still done */
+        for (int a = 0; a < A; ++a) { r[a] = 0.0; d[a] = (uint8_t)((J->done_mask ? J->done_mask[i] >> a : 0) & 1); }
         const int32_t *ad = J->act_d ? J->act_d + (size_t)i * A : 0;
         const double *ac = J->act_c ? J->act_c + (size_t)i * A * 2 : 0;
         for (int t = 0; t < J->ticks_per_step; ++t) {
@@ -383,6 +384,7 @@ static void *ma_step_range(void *arg)
             if (J->term) { double *tm = J->term + 5 * (size_t)i; tm[0] = e.tick; tm[1] = e.nc_obs; tm[2] = e.nc_agent; tm[3] = J->ep_ret[i]; tm[4] = J->ep_len[i]; }
             if (autoreset) { ma_reset(&e); J->ep_ret[i] = 0.0; J->ep_len[i] = 0; }
         }
+        if (J->done_mask) { int m = 0; if (!(any && autoreset)) for (int a = 0; a < A; ++a) m |= d[a] << a; J->done_mask[i] = m; }
         e.overflow |= ma_observe(&e, J->obs + (size_t)i * A * D) ? 0x10000 : 0;
         if (quant) {
             for (int a = 0; a < A; ++a) {
@@ -411,6 +413,7 @@ static void *ma_step_range(void *arg)
 int hw_oracle_ma_step(int n, int A, int K, double *car, int32_t *lane, int32_t *cflags, int32_t *tick, int32_t *leader,
                       int32_t *nobs, double *obst, int32_t *olane, int32_t *ofresh, int32_t *newest,
                       int32_t *nc_obs, int32_t *nc_agent, uint32_t *spawn_ctr, double *ep_ret, int32_t *ep_len, int32_t *overflow,
+                      int32_t *done_mask /* nullable: bit a = car a is done since an earlier step (no auto-reset) */,
                       const int32_t *act_d, const double *act_c, float *obs, double *rew, uint8_t *done, double *term,
                       double dt, int ticks_per_step, int timeout_tick, uint64_t seed, uint64_t env_id0, int hwflags,
                       const double *u_override, int u_stride, int32_t *u_used_out,
@@ -418,7 +421,7 @@ int hw_oracle_ma_step(int n, int A, int K, double *car, int32_t *lane, int32_t *
 {
     if (A < 1 || A > MA_MAX_A || K < 3 || K > MA_MAX_K) return -1;
     ma_job base = { n, A, K, car, lane, cflags, tick, leader, nobs, obst, olane, ofresh, newest, nc_obs, nc_agent, spawn_ctr,
-                    ep_ret, ep_len, overflow, act_d, act_c, obs, rew, done, term, dt, ticks_per_step, timeout_tick, seed, env_id0,
+                    ep_ret, ep_len, overflow, done_mask, act_d, act_c, obs, rew, done, term, dt, ticks_per_step, timeout_tick, seed, env_id0,
                     hwflags, u_override, u_stride, u_used_out, next_car, next_meta, next_obst, next_ometa, 0, n };
     if (nthreads <= 1 || n < 2 * nthreads) { ma_step_range(&base); return 0; }
     if (nthreads > 256) nthreads = 256;

@@ -13,7 +13,7 @@ class MaState(object):
     """canonical multi-agent state for n environments of A cars and up to K live obstacles"""
 
     FIELDS = ("car", "lane", "cflags", "tick", "leader", "nobs", "obst", "olane", "ofresh", "newest",
-              "nc_obs", "nc_agent", "spawn_ctr", "ep_ret", "ep_len", "overflow")
+              "nc_obs", "nc_agent", "spawn_ctr", "ep_ret", "ep_len", "overflow", "done_mask")
 
     def __init__(self, n, A, K=DEFAULT_K):
         self.n, self.A, self.K = n, A, K
@@ -33,6 +33,7 @@ class MaState(object):
         self.ep_ret = np.zeros(n, np.float64)
         self.ep_len = np.zeros(n, np.int32)
         self.overflow = np.zeros(n, np.int32)
+        self.done_mask = np.zeros(n, np.int32)        # bit a: car a finished in an earlier step (persists until reset, no auto-reset only)
 
     def copy(self):
         o = MaState(self.n, self.A, self.K)
@@ -68,6 +69,10 @@ def ma_reset(st, mask=None, want_obs=True):
     rc = L.hw_oracle_ma_reset(*(_state_args(st) + [_p(st.ep_ret, C.c_double), _p(st.ep_len, C.c_int32),
                                                    _p(st.overflow, C.c_int32), _p(mask, C.c_uint8), _p(obs, C.c_float)]))
     assert rc == 0
+    if mask is None:
+        st.done_mask[:] = 0
+    else:
+        st.done_mask[np.asarray(mask).astype(bool)] = 0
     return obs
 
 
@@ -101,7 +106,7 @@ def ma_step(st, actions, continuous=False, real_time=False, seed=0, env_id0=0, i
     L.hw_oracle_ma_step.restype = C.c_int
     rc = L.hw_oracle_ma_step(*(_state_args(st) + [
         _p(st.spawn_ctr, C.c_uint32), _p(st.ep_ret, C.c_double), _p(st.ep_len, C.c_int32), _p(st.overflow, C.c_int32),
-        _p(act_d, C.c_int32), _p(act_c, C.c_double), _p(obs, C.c_float), _p(rew, C.c_double), _p(done, C.c_uint8),
+        _p(st.done_mask, C.c_int32), _p(act_d, C.c_int32), _p(act_c, C.c_double), _p(obs, C.c_float), _p(rew, C.c_double), _p(done, C.c_uint8),
         _p(term, C.c_double), C.c_double(dt), C.c_int(tps), C.c_int(timeout), C.c_uint64(seed), C.c_uint64(env_id0),
         C.c_int(flags), _p(uniforms, C.c_double), C.c_int(u_stride), _p(u_used, C.c_int32),
         _p(nxt.get("next_car"), C.c_double), _p(nxt.get("next_meta"), C.c_int32), _p(nxt.get("next_obst"), C.c_double),

@@ -162,7 +162,12 @@ def test_policy_shapes_on_cpu():
     assert a.shape == (5,) and a.dtype == torch.int32 and v.shape == (5,) and nl.shape == (5,) and (nl > 0).all()
     pc = rollout.MlpPolicy(18, continuous=True)
     a, v, nl = pc.step(torch.rand(5, 18))
-    assert a.shape == (5, 2) and a.abs().max() <= 1.0
+    assert a.shape == (5, 2)
+    # the continuous sample is returned RAW (neglogp belongs to it); only the env's copy is clamped
+    pc.logstd.data.fill_(2.0)
+    a, v, nl = pc.step(torch.rand(4000, 18))
+    mean, _ = pc.forward(torch.rand(1, 18))
+    assert a.abs().max() > 1.0
     assert sum(p.numel() for p in pol.body.parameters()) == 18 * 256 + 256 + 2 * (256 * 256 + 256)
 
 
@@ -178,9 +183,12 @@ def test_policy_bf16_inference_path_and_sampler():
         l16, v16 = pol._forward_bf16(x)
         assert l16.shape == logits.shape and v16.shape == v.shape
         assert (l16 - logits).abs().max() < 5e-3 and (v16 - v).abs().max() < 5e-3
+        ptrs = [w.data_ptr() for w, _ in pol._bf16_body] + [pol._bf16_head_w.data_ptr(), pol._bf16_head_b.data_ptr()]
         pol.pi.bias.add_(1.0)                      # in-place update, as an optimiser step would do
         l16b, _ = pol._forward_bf16(x)
         assert ((l16b - l16) - 1.0).abs().max() < 2e-2
+        # the bf16 copies are refreshed IN PLACE: a CUDA graph holding their addresses stays valid
+        assert [w.data_ptr() for w, _ in pol._bf16_body] + [pol._bf16_head_w.data_ptr(), pol._bf16_head_b.data_ptr()] == ptrs
         # sampler: empirical frequencies of one fixed distribution
         pol.pi.weight.zero_(); pol.pi.bias.copy_(torch.log(torch.tensor([0.1, 0.2, 0.3, 0.4])))
         a, val, nlp = pol.step(torch.rand(200000, 18))
@@ -214,6 +222,28 @@ def test_make_vec_env_rejects_unknown_ids():
     assert ENV_IDS['Highway-v0'] == ('sa', False) and ENV_IDS['MA-Highway-cont-train-v0'] == ('ma', True)
     with pytest.raises(KeyError):
         make_vec_env('CartPole-v0')
+
+
+def test_make_vec_env_gives_every_rank_a_disjoint_env_id_range(monkeypatch):
+    """with the reference's fixed 10000*rank stride two ranks holding 131072 envs each would share most
+    of their Philox streams; the id range of rank r is [start + r*num_env, start + (r+1)*num_env)"""
+    from gym_highway_b200 import cmd_util, vec_env, vec_ma_env
+    seen = []
+
+    class Fake(object):
+        def __init__(self, num_envs, **kw):
+            seen.append((num_envs, kw["env_id0"]))
+    monkeypatch.setattr(vec_env, "HighwayVecEnv", Fake)
+    monkeypatch.setattr(vec_ma_env, "HighwayMAVecEnv", Fake)
+    for rank in range(4):
+        monkeypatch.setenv("RANK", str(rank))
+        cmd_util.make_vec_env('Highway-train-v0', num_env=131072, seed=1, start_index=5)
+        cmd_util.make_vec_env('MA-Highway-train-v0', num_env=16384, seed=1)
+    sa = sorted((lo, lo + n) for n, lo in seen if n == 131072)
+    ma = sorted((lo, lo + n) for n, lo in seen if n == 16384)
+    for rng_ in (sa, ma):
+        assert all(a[1] == b[0] for a, b in zip(rng_, rng_[1:])), rng_   # contiguous, no overlap
+    assert sa[0][0] == 5 and ma[0][0] == 0
 
 
 class _FakeInfos(object):

@@ -100,6 +100,41 @@ def test_trajectory_parity(A, continuous, kernel):
     assert env.episode_statistics()["episodes"] == nd
 
 
+@pytest.mark.parametrize("kernel", ["group"])
+def test_done_flags_persist_without_autoreset(kernel):
+    """gym per-env semantics (HW_FLAG_NO_AUTORESET): `is_done` lives until reset() in the reference (highway_core.py:239, :420),
+    so a car that finished in an earlier step still reports done, and every later step ends after its first tick
+    (highway_env.py:85-86).  ADVICE r1 (low)."""
+    n, A, seed = 1024, 5, 3
+    env = _env(n, A, seed=seed, auto_reset=False, exact_steering=True, kernel=kernel)
+    st = mo.MaState(n, A)
+    mo.ma_reset(st)
+    rng = np.random.RandomState(11)
+    was_done = np.zeros((n, A), bool)
+    tick_prev = np.zeros(n, np.int32)
+    for t in range(45):
+        act = rng.randint(0, 4, (n, A)).astype(np.int32)
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        want = mo.ma_step(st, act, seed=seed, autoreset=False, quantise=True, nthreads=4)
+        d = done.cpu().numpy()
+        assert np.array_equal(d, want["done"]), "done differs at step %d" % t
+        assert bits_equal(obs.cpu().numpy(), want["obs"]) and bits_equal(rew.cpu().numpy(), f32(want["rew"])), t
+        assert (d | ~was_done).all(), "a done flag was dropped at step %d" % t
+        got = _read_state(env)
+        assert np.array_equal(got.tick, st.tick) and np.array_equal(got.done_mask, st.done_mask)
+        # an environment that entered the step with a finished car advances by exactly one tick
+        stale = was_done.any(axis=1)
+        assert np.array_equal((got.tick - tick_prev)[stale], np.ones(int(stale.sum()), np.int32))
+        was_done, tick_prev = d, got.tick.copy()
+    assert was_done.any(axis=1).mean() > 0.5
+    # reset() clears them
+    env.reset(); mo.ma_reset(st)
+    assert int(_read_state(env).done_mask.max()) == 0
+    obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+    want = mo.ma_step(st, act, seed=seed, autoreset=False, quantise=True)
+    assert np.array_equal(done.cpu().numpy(), want["done"]) and not done.any()
+
+
 def test_ma_vecenv_contract():
     env = _env(4, 5, return_numpy=True)
     assert env.num_envs == 4 and env.n == 5 and len(env.observation_space) == 5 and env.observation_space[0].shape == (34,)

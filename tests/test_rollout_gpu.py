@@ -107,6 +107,38 @@ def test_device_runner_zero_copy_rollout(graphed):
     assert (freq - logp.exp().double().mean(0)).abs().max() < 0.02
 
 
+@pytest.mark.parametrize("runner", ["device", "runner_bf16"])
+def test_graph_replay_follows_parameter_updates(runner):
+    """a captured rollout must sample from the CURRENT policy.  The bf16 weight copies are persistent
+    buffers refreshed in place inside run(), so the refresh is part of the graph: after an in-place parameter update
+    (what optimizer.step() does) a replay returns values / neglogpacs of the updated policy, never of the capture-time one."""
+    from gym_highway_b200 import HighwayVecEnv
+    from gym_highway_b200.rollout import MlpPolicy, DeviceRunner, Runner
+    torch.manual_seed(0)
+    n, T = 1024, 8
+    pol = MlpPolicy(18, 4, bf16_inference=(runner == "runner_bf16")).cuda()
+    env = HighwayVecEnv(n, seed=2)
+    run = DeviceRunner(env, pol, nsteps=T, seed=1) if runner == "device" else Runner(env, pol, nsteps=T, generator=None)
+    run.run_graphed()
+    ptrs = [w.data_ptr() for w, _ in pol._bf16_body] + [pol._bf16_head_w.data_ptr()]
+    obs, _, _, actions, values, neglogp = [x.clone() for x in run.run_graphed()[:6]]
+    with torch.no_grad():
+        head = pol.head_bf16(obs).float()
+    assert torch.allclose(values, head[:, 4], atol=1e-6)
+    with torch.no_grad():   # an "optimizer step": every parameter moves, the value head by a lot
+        for p_ in pol.parameters():
+            p_.add_(0.05 * torch.randn_like(p_))
+        pol.vf.bias.add_(3.0)
+    obs2, _, _, actions2, values2, neglogp2 = [x.clone() for x in run.run_graphed()[:6]]
+    assert [w.data_ptr() for w, _ in pol._bf16_body] + [pol._bf16_head_w.data_ptr()] == ptrs  # never rebound
+    with torch.no_grad():
+        head2 = pol.head_bf16(obs2).float()
+    assert torch.allclose(values2, head2[:, 4], atol=1e-6), "the replay used stale weights"
+    assert float((values2.mean() - values.mean()).abs()) > 1.0
+    logp2 = torch.log_softmax(head2[:, :4], dim=-1)
+    assert torch.allclose(neglogp2, -logp2.gather(1, actions2.long().unsqueeze(1)).squeeze(1), atol=2e-3)
+
+
 def test_device_runner_continuous_env():
     """Gaussian sampler + continuous env: stored transitions are the env's own for the clamped actions, neglogpacs follow
     DiagGaussianPd, normals have unit variance"""
