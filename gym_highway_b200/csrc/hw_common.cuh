@@ -70,6 +70,16 @@ __device__ __forceinline__ double dsel3(int sel, double a, double b, double c)
     return r;
 }
 
+// two three-way selects on the same selector (shares the two compares)
+__device__ __forceinline__ void dsel3x2(int sel, double a0, double a1, double a2, double b0, double b1, double b2, double &ra, double &rb)
+{
+    asm("{\n\t.reg .pred p1, p2;\n\tsetp.eq.s32 p1, %8, 1;\n\tsetp.eq.s32 p2, %8, 2;\n\t"
+        "mul.rn.f64 %0, %4, 0d3FF0000000000000;\n\tmul.rn.f64 %1, %7, 0d3FF0000000000000;\n\t"
+        "@!p2 bra HW_T2;\n\tmul.rn.f64 %0, %3, 0d3FF0000000000000;\n\tmul.rn.f64 %1, %6, 0d3FF0000000000000;\nHW_T2:\n\t"
+        "@!p1 bra HW_T1;\n\tmul.rn.f64 %0, %2, 0d3FF0000000000000;\n\tmul.rn.f64 %1, %5, 0d3FF0000000000000;\nHW_T1:\n\t}"
+        : "=&d"(ra), "=&d"(rb) : "d"(a0), "d"(a1), "d"(a2), "d"(b0), "d"(b1), "d"(b2), "r"(sel));
+}
+
 __device__ __forceinline__ void dset_if(bool p, double &x, double c)
 {
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmov.f64 %0, %2;\nHW_SKIP:\n\t}" : "+d"(x) : "r"((int)p), "d"(c));
@@ -123,7 +133,10 @@ constexpr uint32_t kSpawnTag = 0x48574159u;   // "HWAY": obstacle respawn stream
 constexpr uint32_t kActionTag = 0x41435421u;  // "ACT!": in-kernel random-action stream
 
 // out of line on purpose: a respawn is rare, and the ten Philox rounds would otherwise sit in the tick loop
-static __device__ __noinline__ double2 spawn_uniform_pair(uint64_t seed, uint64_t env_id, uint32_t spawn_ctr)
+#ifndef HW_SPAWN_ATTR
+#define HW_SPAWN_ATTR __noinline__
+#endif
+static __device__ HW_SPAWN_ATTR double2 spawn_uniform_pair(uint64_t seed, uint64_t env_id, uint32_t spawn_ctr)
 {
     const uint4 w = philox4x32_10(make_uint4(spawn_ctr, (uint32_t)env_id, (uint32_t)(env_id >> 32), kSpawnTag),
                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
@@ -160,12 +173,15 @@ __device__ __forceinline__ double milli_to_reward(int k, double x)
 // with rc = RN(1/c), which equals the IEEE-rounded x/c for x == 0 and for every float x in [1e-30, c]
 // (verified exhaustively on the host for each constant, scripts/verify_div_by_const.c); x = v - lo
 // cannot fall into (0, 1e-30) unless lo == 0, where GUARD_TINY keeps the IEEE division for that range.
-template <bool GUARD_TINY = false>
+// CLIP = false: the caller guarantees lo <= raw <= hi (np.clip is then the identity and its two compare-selects are dropped).
+template <bool GUARD_TINY = false, bool CLIP = true>
 __device__ __forceinline__ float norm_f32(double raw, const float lo, const float hi)
 {
     float v = (float)raw;  // numpy.array(..., dtype=float32): round to nearest
-    v = (v < lo) ? lo : v;
-    v = (v > hi) ? hi : v;
+    if (CLIP) {
+        v = (v < lo) ? lo : v;
+        v = (v > hi) ? hi : v;
+    }
     const float x = __fsub_rn(v, lo);
     const float c = hi - lo;  // exact for every bound pair of the observation space
     if (c == 8.f || c == 16.f) return __fmul_rn(x, 1.0f / c);
@@ -204,11 +220,16 @@ __device__ __forceinline__ double tan_small(double x)
 // probability ~1e-14 per tick.  EXACT = true (step flag HW_FLAG_EXACT_STEERING) keeps the two IEEE
 // divisions (4/t as 4*(1/t), exact because 4 is a power of two) and is what the bit-exact trajectory tests run.
 template <bool EXACT>
-__device__ __forceinline__ double angular_velocity(double vx, double steer_deg)
+__device__ __forceinline__ double angular_velocity_t(double vx, double t /* tan(radians(steer)) */)
 {
-    const double t = tan_small(dmul(steer_deg, kDeg2Rad));
     if (EXACT) return ddiv(vx, dmul(4.0, __drcp_rn(t)));
     return dmul(dmul(vx, t), 0.25);
+}
+
+template <bool EXACT>
+__device__ __forceinline__ double angular_velocity(double vx, double steer_deg)
+{
+    return angular_velocity_t<EXACT>(vx, tan_small(dmul(steer_deg, kDeg2Rad)));
 }
 
 // Sum over the 32 lanes of a fully converged warp.  Episode counters are accumulated per thread and

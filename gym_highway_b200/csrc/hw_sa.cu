@@ -109,7 +109,18 @@ struct SaConsts {
     int ticks_per_step;
     int timeout_tick;
     double five_dt;  // 5.0 + dt: accelerate() on a clamped acceleration
+    double deg2rad, rad2deg_q;  // pi/180 and 0.25 * 180/pi as launch constants: one LDCU.64 each instead of a UMOV pair per use
 };
+
+// the car's lateral displacement of one tick: degrees(angular_velocity) * dt * dt (multi_lane_sim.py:204-211).
+// Fast mode: angular_velocity = RN(vx*t) * 0.25 and the scaling by 0.25 commutes with the next rounding, so it is folded
+// into the degrees() constant (one DMUL less, same bits).
+template <bool EXACT>
+__device__ __forceinline__ double lateral_step_d(double vx, double t, double dt, const double rad2deg_q)
+{
+    if (EXACT) return dmul(dmul(dmul(angular_velocity_t<true>(vx, t), kRad2Deg), dt), dt);
+    return dmul(dmul(dmul(dmul(vx, t), rad2deg_q), dt), dt);
+}
 
 // respawn (multi_lane_sim.py:963-991): opx < -2.375, pre-filtered on the hi words (negative doubles order reversed)
 __device__ __forceinline__ void sa_respawn(SaEnv &e, const double dt, const bool l1, const bool l2,
@@ -205,11 +216,10 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
         } else if (n0 | n1 | n2) {
             // the car is pinned at x = 10: the x overlap is the interval itself, the y overlap of rect k (y = 21 + 80k,
             // height 38) with the car's rect is |ay - by| <= 37 (see sa_tick_later)
-            const int ay = rect_y(e.py);
-            const bool c0 = n0 && e.opx[0] >= 7.65625 && e.opx[0] < 12.375 && (uint32_t)(ay - 21 + 37) <= 74u;
-            const bool c1 = n1 && e.opx[1] >= 7.65625 && e.opx[1] < 12.375 && (uint32_t)(ay - 101 + 37) <= 74u;
-            const bool c2 = n2 && e.opx[2] >= 7.65625 && e.opx[2] < 12.375 && (uint32_t)(ay - 181 + 37) <= 74u;
-            ncol = (c0 ? 1 : 0) + (c1 ? 1 : 0) + (c2 ? 1 : 0);
+            const int u = rect_y(e.py) + 16;
+            const int k = (int)(((uint32_t)u * 205u) >> 14);
+            const double ox = dsel3(k + 1, e.opx[0], e.opx[1], e.opx[2]);
+            ncol = ((uint32_t)u < 240u) & ((uint32_t)(u - 80 * k) <= 74u) & (ox >= 7.65625) & (ox < 12.375);
             ncoll_acc += ncol;
         }
     }
@@ -246,10 +256,9 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
     }
     const double vdt = dmul(e.vx, dt);
     if (e.steer != 0.0) {
-        const double ang = angular_velocity<EXACT>(e.vx, e.steer);
         // position += velocity * dt has velocity.y == 0: py + 0.0 == py for every py the clamps can produce
-        if (CONT) e.py = dsub(e.py, dmul(ang, dt));
-        else      e.py = dsub(e.py, dmul(dmul(dmul(ang, kRad2Deg), dt), dt));
+        if (CONT) e.py = dsub(e.py, dmul(angular_velocity<EXACT>(e.vx, e.steer), dt));
+        else      e.py = dsub(e.py, lateral_step_d<EXACT>(e.vx, tan_small(dmul(e.steer, K.deg2rad)), dt, K.rad2deg_q));
     }
     e.py = road_clamp<CONT>(e.py);  // with ang == 0, py - 0.0 == py: only the clamp can move it
     e.rx = dadd(e.rx, vdt);
@@ -309,7 +318,8 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     // dlane = -1 / +1 / 0 for LEFT / RIGHT / the other actions is fixed for the step
     lane = (fire & (kBitLeft | kBitRight)) ? min(max(lane + dlane, 1), 3) : lane;
     const bool l1 = lane == 1, l2 = lane == 2, l3 = lane == 3;
-    const double fpx = dsel3(lane, e.opx[0], e.opx[1], e.opx[2]), fiv = dsel3(lane, e.oiv[0], e.oiv[1], e.oiv[2]);
+    double fpx, fiv;
+    dsel3x2(lane, e.opx[0], e.opx[1], e.opx[2], e.oiv[0], e.oiv[1], e.oiv[2], fpx, fiv);
     {
         // maintain(): cruise = velocity of the vehicle ahead in the lane, else the car's own.  An obstacle that was held
         // back in the previous tick (e.slow) moved by fl(fl(x + vdt) - vdt) <= 10 from x < 10, so one that is ahead
@@ -330,11 +340,12 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
         constexpr uint32_t kLo = 0x401EA000u, kSpan = 0x4028C000u - 0x401EA000u;  // hi(7.65625), hi(12.375)
         const bool n0 = hi32(e.opx[0]) - kLo <= kSpan, n1 = hi32(e.opx[1]) - kLo <= kSpan, n2 = hi32(e.opx[2]) - kLo <= kSpan;
         if (n0 | n1 | n2) {
-            const int ay = rect_y(e.py);
-            const bool c0 = n0 && e.opx[0] >= 7.65625 && e.opx[0] < 12.375 && (uint32_t)(ay - 21 + 37) <= 74u;
-            const bool c1 = n1 && e.opx[1] >= 7.65625 && e.opx[1] < 12.375 && (uint32_t)(ay - 101 + 37) <= 74u;
-            const bool c2 = n2 && e.opx[2] >= 7.65625 && e.opx[2] < 12.375 && (uint32_t)(ay - 181 + 37) <= 74u;
-            ncol = (c0 ? 1 : 0) + (c1 ? 1 : 0) + (c2 ? 1 : 0);
+            // rect k (y = 21 + 80k, height 38) overlaps the car's rect in y iff |ay - (21 + 80k)| <= 37; the three windows are
+            // disjoint, so at most ONE lane can collide: pick it from ay and test that obstacle alone
+            const int u = rect_y(e.py) + 16;                        // window k is u in [80k, 80k + 74]
+            const int k = (int)(((uint32_t)u * 205u) >> 14);        // u / 80 for 0 <= u < 240
+            const double ox = dsel3(k + 1, e.opx[0], e.opx[1], e.opx[2]);
+            ncol = ((uint32_t)u < 240u) & ((uint32_t)(u - 80 * k) <= 74u) & (ox >= 7.65625) & (ox < 12.375);
             ncoll_acc += ncol;
         }
     }
@@ -381,10 +392,9 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
         dset_if(reached, st, 0.0);
         if (reached) b &= ~(kBitLeft | kBitRight);
         e.steer = st;
-        if (st != 0.0) {
-            const double ang = angular_velocity<EXACT>(e.vx, st);
-            e.py = road_clamp<false>(dsub(e.py, dmul(dmul(dmul(ang, kRad2Deg), dt), dt)));
-        }
+        // when the lane has just been reached st is 0: tan(0) = 0, the step is 0 (also through the exact path's vx / inf) and
+        // py - 0 = py lies inside the road clamp already - no second branch around the steering arithmetic
+        e.py = road_clamp<false>(dsub(e.py, lateral_step_d<EXACT>(e.vx, tan_small(dmul(st, K.deg2rad)), dt, K.rad2deg_q)));
     }
     e.bits = b;
 
@@ -411,18 +421,24 @@ __device__ __forceinline__ void sa_materialise_ovx(SaEnv &e)
     for (int k = 0; k < 3; ++k) e.ovx[k] = (e.slow && lane == k + 1) ? e.vx : e.oiv[k];
 }
 
-// observation pairs (x, y) j = 0..8 -> obs[2j], obs[2j+1]; float32 clip + normalise
+// observation pairs (x, y) j = 0..8 -> obs[2j], obs[2j+1]; float32 clip + normalise.
+// STEPPED = true (the state has just gone through at least one tick, or is the start grid): py is in [0, 7], vx in [0, 20]
+// and every obstacle velocity is its init_vx (5..7, DESIGN.md deviation 5) or the car's vx, so np.clip is the identity on
+// py, the three lane offsets, vx and the three relative velocities - 16 compare-selects per step the kernel does not issue.
+// acc (<= 5 + dt), steer (<= 30 + 30*dt), raw x (<= 1220) and the obstacle distances (spawns 70..100 ahead) do clip.
+template <bool STEPPED>
 __device__ __forceinline__ void sa_observe(const SaEnv &e, float2 *row)
 {
+    constexpr bool C = !STEPPED;
     row[0] = make_float2(norm_f32(e.acc, -5.f, 5.f), norm_f32(e.steer, -30.f, 30.f));
-    row[1] = make_float2(norm_f32<true>(e.rx, 0.f, 1200.f), norm_f32(e.py, 0.f, 8.f));
+    row[1] = make_float2(norm_f32<true>(e.rx, 0.f, 1200.f), norm_f32<false, C>(e.py, 0.f, 8.f));
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         row[2 + k] = make_float2(norm_f32(dsub(e.orx[k], e.rx), -60.f, 60.f),
-                                 norm_f32(dsub(lane_centre(k), e.py), -8.f, 8.f));
-        row[6 + k] = make_float2(norm_f32(dsub(e.ovx[k], e.vx), -20.f, 20.f), 0.5f);
+                                 norm_f32<false, C>(dsub(lane_centre(k), e.py), -8.f, 8.f));
+        row[6 + k] = make_float2(norm_f32<false, C>(dsub(e.ovx[k], e.vx), -20.f, 20.f), 0.5f);
     }
-    row[5] = make_float2(norm_f32(e.vx, -20.f, 20.f), 0.5f);
+    row[5] = make_float2(norm_f32<false, C>(e.vx, -20.f, 20.f), 0.5f);
 }
 
 // One warp's observations (32 rows x 18 floats = 2304 contiguous bytes in global memory) go through a
@@ -536,37 +552,68 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
             is_done = timeout || ncol > 0;
             reward = (ncol > 0) ? -250.0 * (double)ncol : dsub(ddiv_const(e.vx, 20.0), 1.0);
             rew_milli = round_milli(reward);
-            ret_milli_step += rew_milli;
-            len_step += 1;
-            sa_materialise_ovx(e);
-
-            if (is_done) {
-                // Monitor / info of the finished episode: state counters + what this launch added
-                const uint4 st = S.stat[i];
-                const uint32_t nc = (was_reset ? 0u : st.x) + ncoll_step;
-                const int er = (was_reset ? 0 : (int)st.z) + ret_milli_step;
-                const uint32_t el = (was_reset ? 0u : st.w) + len_step;
-                if (term) term[i] = make_int4((int)tick, (int)nc, er, (int)el);
-                acc_eps += 1; acc_len += el; acc_ret += er; acc_col += nc; acc_to += (ncol == 0) ? 1 : 0;
-                if (autoreset) {
-                    sa_reset_env(e);
-                    was_reset = true; ncoll_step = 0; ret_milli_step = 0; len_step = 0;
-                } else if (tick >= 0xFF00u) {
+            if (!RANDOM_ACTIONS) {
+                // ---- epilogue of step() proper (one step per launch) ----
+                // The finished-episode path never merges with the live state: an auto-reset environment stores the start grid
+                // and its observation (constants), every other one stores what the ticks left.  (With the reset written as
+                // `e = start grid` ahead of a common store, ptxas spilled the whole 19-double state around the branch.)
+                rew[i] = (float)milli_to_reward(rew_milli, reward);
+                done[i] = is_done ? 1 : 0;
+                float2 *row = reinterpret_cast<float2 *>(sm_tile) + (threadIdx.x & 31) * (HW_SA_OBS_DIM / 2);
+                uint4 st = S.stat[i];  // per-env counters: read-modify-write once per launch
+                st.x += ncoll_step; st.y = e.spawn_ctr; st.z = (uint32_t)((int)st.z + rew_milli); st.w += 1;
+                if (is_done) {  // Monitor / info of the finished episode
+                    if (term) term[i] = make_int4((int)tick, (int)st.x, (int)st.z, (int)st.w);
+                    acc_eps += 1; acc_len += st.w; acc_ret += (int)st.z; acc_col += st.x; acc_to += (ncol == 0) ? 1 : 0;
+                }
+                if (is_done && autoreset) {
+                    SaEnv r;
+                    sa_reset_env(r);
+                    r.spawn_ctr = 0;
+                    sa_observe<false>(r, row);
+                    sa_store(r, S, i, n);
+                    st.x = 0; st.z = 0; st.w = 0;
+                } else {
                     // gym per-env semantics (no auto-reset) stepped far past the time-out: the 16-bit tick field saturates
                     // instead of carrying into the lane bits (the episode has been over for 60000 ticks; only `done` matters)
-                    e.bits = (e.bits & ~HW_BITS_TICK_MASK) | 0xFF00u;
+                    if (tick >= 0xFF00u) e.bits = (e.bits & ~HW_BITS_TICK_MASK) | 0xFF00u;
+                    sa_materialise_ovx(e);
+                    sa_observe<true>(e, row);
+                    sa_store(e, S, i, n);
+                }
+                S.stat[i] = st;
+            } else {
+                ret_milli_step += rew_milli;
+                len_step += 1;
+                sa_materialise_ovx(e);
+                if (is_done) {
+                    // Monitor / info of the finished episode: state counters + what this launch added
+                    const uint4 st = S.stat[i];
+                    const uint32_t nc = (was_reset ? 0u : st.x) + ncoll_step;
+                    const int er = (was_reset ? 0 : (int)st.z) + ret_milli_step;
+                    const uint32_t el = (was_reset ? 0u : st.w) + len_step;
+                    if (term) term[i] = make_int4((int)tick, (int)nc, er, (int)el);
+                    acc_eps += 1; acc_len += el; acc_ret += er; acc_col += nc; acc_to += (ncol == 0) ? 1 : 0;
+                    if (autoreset) {
+                        sa_reset_env(e);
+                        was_reset = true; ncoll_step = 0; ret_milli_step = 0; len_step = 0;
+                    } else if (tick >= 0xFF00u) {
+                        e.bits = (e.bits & ~HW_BITS_TICK_MASK) | 0xFF00u;
+                    }
                 }
             }
         }
-        rew[i] = (float)milli_to_reward(rew_milli, reward);
-        done[i] = is_done ? 1 : 0;
-        sa_observe(e, reinterpret_cast<float2 *>(sm_tile) + (threadIdx.x & 31) * (HW_SA_OBS_DIM / 2));
-        sa_store(e, S, i, n);
-        {   // per-env counters: read-modify-write once per launch
-            uint4 st = S.stat[i];
-            if (was_reset) { st.x = 0; st.z = 0; st.w = 0; }
-            st.x += ncoll_step; st.y = e.spawn_ctr; st.z = (uint32_t)((int)st.z + ret_milli_step); st.w += len_step;
-            S.stat[i] = st;
+        if (RANDOM_ACTIONS) {
+            rew[i] = (float)milli_to_reward(rew_milli, reward);
+            done[i] = is_done ? 1 : 0;
+            sa_observe<true>(e, reinterpret_cast<float2 *>(sm_tile) + (threadIdx.x & 31) * (HW_SA_OBS_DIM / 2));
+            sa_store(e, S, i, n);
+            {   // per-env counters: read-modify-write once per launch
+                uint4 st = S.stat[i];
+                if (was_reset) { st.x = 0; st.z = 0; st.w = 0; }
+                st.x += ncoll_step; st.y = e.spawn_ctr; st.z = (uint32_t)((int)st.z + ret_milli_step); st.w += len_step;
+                S.stat[i] = st;
+            }
         }
     }
     store_obs_warp(sm_tile, obs, warp_base, n);
@@ -597,7 +644,7 @@ sa_reset_kernel(SaPtrs S, const uint8_t *__restrict__ mask, float *__restrict__ 
     S.stat[i] = make_uint4(0u, S.stat[i].y, 0u, 0u);  // spawn_ctr survives so that every episode sees fresh obstacles
     if (obs) {
         float2 row[9];
-        sa_observe(e, row);
+        sa_observe<false>(e, row);
         float2 *dst = reinterpret_cast<float2 *>(obs + i * HW_SA_OBS_DIM);
 #pragma unroll
         for (int j = 0; j < 9; ++j) dst[j] = row[j];
@@ -615,7 +662,7 @@ sa_observe_kernel(SaPtrs S, float *__restrict__ obs, const int64_t n)
     if (i < n) {
         SaEnv e;
         sa_load(e, S, i, n);
-        sa_observe(e, reinterpret_cast<float2 *>(sm_tile) + (threadIdx.x & 31) * (HW_SA_OBS_DIM / 2));
+        sa_observe<false>(e, reinterpret_cast<float2 *>(sm_tile) + (threadIdx.x & 31) * (HW_SA_OBS_DIM / 2));
     }
     store_obs_warp(sm_tile, obs, warp_base, n);
 }
@@ -665,6 +712,8 @@ static int launch_step_range(const HwSaState *st, const void *actions, const HwS
     K.dt = P->dt;
     K.k30dt = 30.0 * P->dt;  // python: 30.0 * dt
     K.five_dt = 5.0 + P->dt;
+    K.deg2rad = kDeg2Rad;
+    K.rad2deg_q = 0.25 * kRad2Deg;  // exact scaling of the constant
     K.ticks_per_step = P->ticks_per_step;
     K.timeout_tick = P->timeout_tick;
     const unsigned grid = (unsigned)((count + kSaBlock - 1) / kSaBlock);
