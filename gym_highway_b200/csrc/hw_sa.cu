@@ -17,7 +17,7 @@
 namespace hw {
 
 #ifndef HW_SA_BLOCK
-#define HW_SA_BLOCK 128
+#define HW_SA_BLOCK 64   // two warps per block: warps never synchronise with each other, small blocks only shorten the tail
 #endif
 constexpr int kSaBlock = HW_SA_BLOCK;
 
@@ -33,31 +33,32 @@ struct SaEnv {
 };
 
 struct SaPtrs {
-    float4 *car_a, *car_b, *obst;
+    float4 *car_a, *car_b;
+    float4 *obst0, *obst1, *obst2;  // the three lanes of `obst` (batch-size apart; a launch may cover a sub-range)
     uint4 *stat;
-    int64_t ostride;  // environments between the lanes of `obst` (the batch size; a launch may cover a sub-range)
 };
 
-__device__ __forceinline__ void sa_load(SaEnv &e, const SaPtrs &S, int64_t i, int64_t n)
+// environments are indexed with 32 bits (a launch covers < 2^31 of them): one IMAD.WIDE per address instead of a 64-bit add chain
+__device__ __forceinline__ void sa_load(SaEnv &e, const SaPtrs &S, uint32_t i)
 {
     const float4 a = S.car_a[i], b = S.car_b[i];
-    const float4 o0 = S.obst[i], o1 = S.obst[S.ostride + i], o2 = S.obst[2 * S.ostride + i];
+    const float4 o0 = S.obst0[i], o1 = S.obst1[i], o2 = S.obst2[i];
     e.px = a.x; e.py = a.y; e.rx = a.z; e.vx = a.w;
     e.acc = b.x; e.steer = b.y; e.cruise = b.z; e.bits = __float_as_uint(b.w);
     e.opx[0] = o0.x; e.orx[0] = o0.y; e.ovx[0] = o0.z; e.oiv[0] = o0.w;
     e.opx[1] = o1.x; e.orx[1] = o1.y; e.ovx[1] = o1.z; e.oiv[1] = o1.w;
     e.opx[2] = o2.x; e.orx[2] = o2.y; e.ovx[2] = o2.z; e.oiv[2] = o2.w;
-    e.spawn_ctr = reinterpret_cast<const uint32_t *>(S.stat)[4 * i + 1];  // the other counters are touched once, at the end
+    e.spawn_ctr = reinterpret_cast<const uint32_t *>(S.stat + i)[1];  // the other counters are touched once, at the end
     e.slow = false;
 }
 
-__device__ __forceinline__ void sa_store(const SaEnv &e, const SaPtrs &S, int64_t i, int64_t n)
+__device__ __forceinline__ void sa_store(const SaEnv &e, const SaPtrs &S, uint32_t i)
 {
     S.car_a[i] = make_float4((float)e.px, (float)e.py, (float)e.rx, (float)e.vx);
     S.car_b[i] = make_float4((float)e.acc, (float)e.steer, (float)e.cruise, __uint_as_float(e.bits));
-    S.obst[i] = make_float4((float)e.opx[0], (float)e.orx[0], (float)e.ovx[0], (float)e.oiv[0]);
-    S.obst[S.ostride + i] = make_float4((float)e.opx[1], (float)e.orx[1], (float)e.ovx[1], (float)e.oiv[1]);
-    S.obst[2 * S.ostride + i] = make_float4((float)e.opx[2], (float)e.orx[2], (float)e.ovx[2], (float)e.oiv[2]);
+    S.obst0[i] = make_float4((float)e.opx[0], (float)e.orx[0], (float)e.ovx[0], (float)e.oiv[0]);
+    S.obst1[i] = make_float4((float)e.opx[1], (float)e.orx[1], (float)e.ovx[1], (float)e.oiv[1]);
+    S.obst2[i] = make_float4((float)e.opx[2], (float)e.orx[2], (float)e.ovx[2], (float)e.oiv[2]);
 }
 
 // start grid, highway_env.py:55-65
@@ -109,6 +110,7 @@ struct SaConsts {
     int ticks_per_step;
     int timeout_tick;
     double five_dt;  // 5.0 + dt: accelerate() on a clamped acceleration
+    uint32_t respawn_hi;  // hi word of the respawn threshold -2.375, or 0xFFFFFFFF (never) with inf_obs=False: the flag costs nothing per tick
     double deg2rad, rad2deg_q;  // pi/180 and 0.25 * 180/pi as launch constants: one LDCU.64 each instead of a UMOV pair per use
 };
 
@@ -123,10 +125,10 @@ __device__ __forceinline__ double lateral_step_d(double vx, double t, double dt,
 }
 
 // respawn (multi_lane_sim.py:963-991): opx < -2.375, pre-filtered on the hi words (negative doubles order reversed)
-__device__ __forceinline__ void sa_respawn(SaEnv &e, const double dt, const bool l1, const bool l2,
+__device__ __forceinline__ void sa_respawn(SaEnv &e, const uint32_t kNeg, const bool l1, const bool l2,
                                            const uint64_t seed, const uint64_t env_id)
 {
-    constexpr uint32_t kNeg = 0xC0030000u;  // hi(-2.375); hi >= kNeg  <=>  opx <= -2.375 (- a few ulps of slack)
+    // kNeg = 0xC0030000 = hi(-2.375); hi >= kNeg  <=>  opx <= -2.375 (- a few ulps of slack)
     if (max(max(hi32(e.opx[0]), hi32(e.opx[1])), hi32(e.opx[2])) >= kNeg) {
         // lanes in ascending order; x = U(70,100) then v = U(5,7) from one Philox block per spawn
 #pragma unroll 1
@@ -288,7 +290,7 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
     }
 
     // ---- respawn (:963-991) ----
-    if (inf_obs) sa_respawn(e, dt, l1, l2, seed, env_id);
+    sa_respawn(e, K.respawn_hi, l1, l2, seed, env_id);
     return ncol;
 }
 
@@ -409,7 +411,7 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     }
 
     // ---- respawn (:963-991) ----
-    if (inf_obs) sa_respawn(e, dt, l1, l2, seed, env_id);
+    sa_respawn(e, K.respawn_hi, l1, l2, seed, env_id);
     return ncol;
 }
 
@@ -421,55 +423,109 @@ __device__ __forceinline__ void sa_materialise_ovx(SaEnv &e)
     for (int k = 0; k < 3; ++k) e.ovx[k] = (e.slow && lane == k + 1) ? e.vx : e.oiv[k];
 }
 
+// Where an observation row goes.  SmRow: the lane's row of the warp-private shared-memory tile, addressed in the shared
+// state space with a 32-bit address (a generic float2* made ptxas rebuild the shared window base - S2R CgaCtaId, LEA, IMAD -
+// at every group of stores); PtrRow: plain memory (reset kernel).
+struct SmRow {
+    uint32_t addr;
+    __device__ __forceinline__ void put(int j, float2 v) const
+    {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(addr + 8u * (uint32_t)j), "f"(v.x), "f"(v.y) : "memory");
+    }
+};
+struct PtrRow {
+    float2 *p;
+    __device__ __forceinline__ void put(int j, float2 v) const { p[j] = v; }
+};
+
 // observation pairs (x, y) j = 0..8 -> obs[2j], obs[2j+1]; float32 clip + normalise.
 // STEPPED = true (the state has just gone through at least one tick, or is the start grid): py is in [0, 7], vx in [0, 20]
 // and every obstacle velocity is its init_vx (5..7, DESIGN.md deviation 5) or the car's vx, so np.clip is the identity on
 // py, the three lane offsets, vx and the three relative velocities - 16 compare-selects per step the kernel does not issue.
 // acc (<= 5 + dt), steer (<= 30 + 30*dt), raw x (<= 1220) and the obstacle distances (spawns 70..100 ahead) do clip.
-template <bool STEPPED>
-__device__ __forceinline__ void sa_observe(const SaEnv &e, float2 *row)
+template <bool STEPPED, class Row>
+__device__ __forceinline__ void sa_observe(const SaEnv &e, const Row row)
 {
     constexpr bool C = !STEPPED;
-    row[0] = make_float2(norm_f32(e.acc, -5.f, 5.f), norm_f32(e.steer, -30.f, 30.f));
-    row[1] = make_float2(norm_f32<true>(e.rx, 0.f, 1200.f), norm_f32<false, C>(e.py, 0.f, 8.f));
+    row.put(0, make_float2(norm_f32(e.acc, -5.f, 5.f), norm_f32(e.steer, -30.f, 30.f)));
+    row.put(1, make_float2(norm_f32<true>(e.rx, 0.f, 1200.f), norm_f32<false, C>(e.py, 0.f, 8.f)));
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        row[2 + k] = make_float2(norm_f32(dsub(e.orx[k], e.rx), -60.f, 60.f),
-                                 norm_f32<false, C>(dsub(lane_centre(k), e.py), -8.f, 8.f));
-        row[6 + k] = make_float2(norm_f32<false, C>(dsub(e.ovx[k], e.vx), -20.f, 20.f), 0.5f);
+        row.put(2 + k, make_float2(norm_f32(dsub(e.orx[k], e.rx), -60.f, 60.f),
+                                   norm_f32<false, C>(dsub(lane_centre(k), e.py), -8.f, 8.f)));
+        row.put(6 + k, make_float2(norm_f32<false, C>(dsub(e.ovx[k], e.vx), -20.f, 20.f), 0.5f));
     }
-    row[5] = make_float2(norm_f32<false, C>(e.vx, -20.f, 20.f), 0.5f);
+    row.put(5, make_float2(norm_f32<false, C>(e.vx, -20.f, 20.f), 0.5f));
+}
+
+// Observation + state store of an environment that has just been stepped (no reset), without materialising ovx[] in
+// fp64: the velocity an obstacle had after its last update is its init_vx, except for the one that is being held back
+// behind the car (`slow`, in the car's lane), which moved with the car's vx - its relative velocity is exactly 0 -> 0.5.
+__device__ __forceinline__ void sa_finish_stepped(const SaEnv &e, const SmRow row, const SaPtrs &S, uint32_t i)
+{
+    const int held = e.slow ? (int)((e.bits >> HW_BITS_LANE_SHIFT) & 3u) : 0;
+    const float vxf = (float)e.vx, pyf = (float)e.py, rxf = (float)e.rx, accf = (float)e.acc, steerf = (float)e.steer;
+    row.put(0, make_float2(norm_f32(e.acc, -5.f, 5.f), norm_f32(e.steer, -30.f, 30.f)));
+    row.put(1, make_float2(norm_f32<true>(e.rx, 0.f, 1200.f), norm_f32<false, false>(e.py, 0.f, 8.f)));
+    row.put(5, make_float2(norm_f32<false, false>(e.vx, -20.f, 20.f), 0.5f));
+    float ovf[3], oif[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        row.put(2 + k, make_float2(norm_f32(dsub(e.orx[k], e.rx), -60.f, 60.f),
+                                   norm_f32<false, false>(dsub(lane_centre(k), e.py), -8.f, 8.f)));
+        const float dv = norm_f32<false, false>(dsub(e.oiv[k], e.vx), -20.f, 20.f);
+        row.put(6 + k, make_float2(held == k + 1 ? 0.5f : dv, 0.5f));
+        oif[k] = (float)e.oiv[k];
+        ovf[k] = held == k + 1 ? vxf : oif[k];
+    }
+    S.car_a[i] = make_float4((float)e.px, pyf, rxf, vxf);
+    S.car_b[i] = make_float4(accf, steerf, (float)e.cruise, __uint_as_float(e.bits));
+    S.obst0[i] = make_float4((float)e.opx[0], (float)e.orx[0], ovf[0], oif[0]);
+    S.obst1[i] = make_float4((float)e.opx[1], (float)e.orx[1], ovf[1], oif[1]);
+    S.obst2[i] = make_float4((float)e.opx[2], (float)e.orx[2], ovf[2], oif[2]);
 }
 
 // One warp's observations (32 rows x 18 floats = 2304 contiguous bytes in global memory) go through a
 // warp-private shared-memory tile: each lane writes its row as nine 8-byte words (conflict-free: the row
 // stride is 9 words of 8 bytes, odd), then the warp streams the tile out as 144 coalesced 16-byte stores.
 // Only __syncwarp() is needed, so warps never wait for each other.
-__device__ __forceinline__ void store_obs_warp(float *sm_tile, float *__restrict__ obs, int64_t warp_base, int64_t n)
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// tile_s: shared-state-space address of the warp's tile
+__device__ __forceinline__ void store_obs_warp(const uint32_t tile_s, float *__restrict__ obs, int64_t warp_base, int64_t n)
 {
     __syncwarp();
-    const int lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31;
     const int64_t rows = min((int64_t)32, n - warp_base);
     float *dst = obs + warp_base * HW_SA_OBS_DIM;
     if (rows == 32) {
-        const float4 *src = reinterpret_cast<const float4 *>(sm_tile);
         float4 *d4 = reinterpret_cast<float4 *>(dst);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) d4[lane + 32 * v] = src[lane + 32 * v];
-        if (lane < 16) d4[lane + 128] = src[lane + 128];
+        for (int v = 0; v < 4; ++v) d4[lane + 32 * v] = lds128(tile_s + 16u * (lane + 32 * v));
+        if (lane < 16) d4[lane + 128] = lds128(tile_s + 16u * (lane + 128));
     } else {
-        for (int f = lane; f < (int)rows * HW_SA_OBS_DIM; f += 32) dst[f] = sm_tile[f];
+        for (uint32_t f = lane; f < (uint32_t)rows * HW_SA_OBS_DIM; f += 32) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(tile_s + 4u * f) : "memory");
+            dst[f] = v;
+        }
     }
 }
 
-// Resident blocks per SM the register allocator is asked to make room for: 8 blocks of 128 threads = 64 registers per
-// thread = 32 warps/SM.  Measured on B200 at 4M envs with the round-1 final tick (discrete): 7 blocks (72 registers)
-// 316 us, 8 blocks 307 us, 9 blocks (56 registers, spills) 374 us, 10 blocks 399 us; 64- and 256-thread blocks within 1 %.
+// Resident blocks per SM the register allocator is asked to make room for: 16 blocks of 64 threads = 64 registers per
+// thread = 32 warps/SM.  Measured on B200 at 4M envs (discrete): round 1, 128-thread blocks: 7 blocks (72 registers) 316 us,
+// 8 blocks 307 us, 9 blocks (56 registers, spills) 374 us, 10 blocks 399 us; round 2 (spill-free kernel): 256-thread blocks
+// 298.9 us, 128-thread 290.8 - 294.8 us, 64-thread 288.8 - 292.8 us, 72 registers 292.9 us (continuous 268 vs 258 us).
 #ifndef HW_SA_MIN_BLOCKS_D
-#define HW_SA_MIN_BLOCKS_D 8
+#define HW_SA_MIN_BLOCKS_D (2048 / HW_SA_BLOCK / 2)
 #endif
 #ifndef HW_SA_MIN_BLOCKS_C
-#define HW_SA_MIN_BLOCKS_C 8
+#define HW_SA_MIN_BLOCKS_C (2048 / HW_SA_BLOCK / 2)
 #endif
 
 template <bool CONT, bool RANDOM_ACTIONS, bool EXACT>
@@ -482,9 +538,9 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
     const int steps = RANDOM_ACTIONS ? steps_arg : 1;  // step() proper is one step per launch: lets the episode bookkeeping fold
 
     __shared__ __align__(16) float sm_obs[kSaBlock * HW_SA_OBS_DIM];
-    const int64_t i = (int64_t)blockIdx.x * kSaBlock + threadIdx.x;
-    const int64_t warp_base = i - (threadIdx.x & 31);
-    float *sm_tile = sm_obs + (threadIdx.x >> 5) * 32 * HW_SA_OBS_DIM;
+    const uint32_t i = blockIdx.x * kSaBlock + threadIdx.x;  // < 2^31, checked by the launcher
+    const int64_t warp_base = (int64_t)(i - (threadIdx.x & 31));
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(sm_obs) + (threadIdx.x >> 5) * (32 * HW_SA_OBS_DIM * 4);
     if (warp_base >= n) return;  // whole warp out of range
     const bool inf_obs = !(flags & HW_FLAG_NO_INF_OBS);
     const bool autoreset = !(flags & HW_FLAG_NO_AUTORESET);
@@ -493,7 +549,7 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
 
     if (i < n) {
         SaEnv e;
-        sa_load(e, S, i, n);
+        sa_load(e, S, i);
         const uint64_t env_id = env_id0 + (uint64_t)i;
 
         // episode accounting (Monitor) lives outside the tick loop
@@ -530,9 +586,13 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                 act_d = reinterpret_cast<const int *>(actions)[i];
             }
             if (!CONT) {  // ACTION_LOOKUP (highway_env.py:14-20) as the mode bit it requests
-                amask = (act_d == HW_ACT_LEFT) ? kBitLeft : (act_d == HW_ACT_RIGHT) ? kBitRight
-                      : (act_d == HW_ACT_ACCELERATE) ? kBitDoAcc : (act_d == HW_ACT_MAINTAIN) ? kBitDoMaint : 0u;
-                apair = (amask & (kBitLeft | kBitRight)) ? (kBitLeft | kBitRight) : amask ? (kBitDoAcc | kBitDoMaint) : 0u;
+                // LEFT, RIGHT, ACCELERATE, MAINTAIN = 0..3 ask for the mode bits 18..21 in that order: shifts instead of a
+                // four-way select (which nvcc turns into a divergent jump table); any other value requests nothing
+                static_assert(HW_ACT_LEFT == 0 && HW_ACT_RIGHT == 1 && HW_ACT_ACCELERATE == 2 && HW_ACT_MAINTAIN == 3, "action codes");
+                static_assert(kBitRight == kBitLeft << 1 && kBitDoAcc == kBitLeft << 2 && kBitDoMaint == kBitLeft << 3, "mode bits");
+                const bool valid = (uint32_t)act_d < 4u;
+                amask = valid ? (kBitLeft << (act_d & 3)) : 0u;
+                apair = valid ? ((kBitLeft | kBitRight) << (act_d & 2)) : 0u;
             }
             // env.step: up to ticks_per_step ticks, stop at the first crash (highway_env.py:99-108)
             int ncol = sa_tick<CONT, true, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
@@ -542,7 +602,7 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                     ncol = sa_tick<CONT, false, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
             } else {
                 int lane = (int)((e.bits >> HW_BITS_LANE_SHIFT) & 3u);
-                const int dlane = (act_d == HW_ACT_RIGHT) ? 1 : (act_d == HW_ACT_LEFT) ? -1 : 0;
+                const int dlane = ((uint32_t)act_d < 2u) ? 2 * act_d - 1 : 0;  // LEFT -1, RIGHT +1
                 for (int t = 1; t < K.ticks_per_step && ncol == 0; ++t)
                     ncol = sa_tick_later<EXACT>(e, lane, ncoll_step, K, inf_obs, amask, apair, dlane, seed, env_id);
                 e.bits = (e.bits & ~(3u << HW_BITS_LANE_SHIFT)) | ((uint32_t)lane << HW_BITS_LANE_SHIFT);
@@ -550,7 +610,8 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
             const uint32_t tick = e.bits & HW_BITS_TICK_MASK;
             const bool timeout = tick >= (uint32_t)K.timeout_tick;
             is_done = timeout || ncol > 0;
-            reward = (ncol > 0) ? -250.0 * (double)ncol : dsub(ddiv_const(e.vx, 20.0), 1.0);
+            // the three lanes' rect windows are disjoint in y: a tick counts at most one overlapping obstacle, so -250 * n is -250
+            reward = (ncol > 0) ? -250.0 : dsub(ddiv_const(e.vx, 20.0), 1.0);
             rew_milli = round_milli(reward);
             if (!RANDOM_ACTIONS) {
                 // ---- epilogue of step() proper (one step per launch) ----
@@ -559,7 +620,7 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                 // `e = start grid` ahead of a common store, ptxas spilled the whole 19-double state around the branch.)
                 rew[i] = (float)milli_to_reward(rew_milli, reward);
                 done[i] = is_done ? 1 : 0;
-                float2 *row = reinterpret_cast<float2 *>(sm_tile) + (threadIdx.x & 31) * (HW_SA_OBS_DIM / 2);
+                const SmRow row{tile_s + (threadIdx.x & 31) * (HW_SA_OBS_DIM * 4)};
                 uint4 st = S.stat[i];  // per-env counters: read-modify-write once per launch
                 st.x += ncoll_step; st.y = e.spawn_ctr; st.z = (uint32_t)((int)st.z + rew_milli); st.w += 1;
                 if (is_done) {  // Monitor / info of the finished episode
@@ -571,15 +632,13 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                     sa_reset_env(r);
                     r.spawn_ctr = 0;
                     sa_observe<false>(r, row);
-                    sa_store(r, S, i, n);
+                    sa_store(r, S, i);
                     st.x = 0; st.z = 0; st.w = 0;
                 } else {
                     // gym per-env semantics (no auto-reset) stepped far past the time-out: the 16-bit tick field saturates
                     // instead of carrying into the lane bits (the episode has been over for 60000 ticks; only `done` matters)
                     if (tick >= 0xFF00u) e.bits = (e.bits & ~HW_BITS_TICK_MASK) | 0xFF00u;
-                    sa_materialise_ovx(e);
-                    sa_observe<true>(e, row);
-                    sa_store(e, S, i, n);
+                    sa_finish_stepped(e, row, S, i);
                 }
                 S.stat[i] = st;
             } else {
@@ -606,8 +665,8 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
         if (RANDOM_ACTIONS) {
             rew[i] = (float)milli_to_reward(rew_milli, reward);
             done[i] = is_done ? 1 : 0;
-            sa_observe<true>(e, reinterpret_cast<float2 *>(sm_tile) + (threadIdx.x & 31) * (HW_SA_OBS_DIM / 2));
-            sa_store(e, S, i, n);
+            sa_observe<true>(e, SmRow{tile_s + (threadIdx.x & 31) * (HW_SA_OBS_DIM * 4)});
+            sa_store(e, S, i);
             {   // per-env counters: read-modify-write once per launch
                 uint4 st = S.stat[i];
                 if (was_reset) { st.x = 0; st.z = 0; st.w = 0; }
@@ -616,7 +675,7 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
             }
         }
     }
-    store_obs_warp(sm_tile, obs, warp_base, n);
+    store_obs_warp(tile_s, obs, warp_base, n);
     if (stats && __any_sync(0xffffffffu, acc_eps != 0)) {  // all 32 lanes are here (warps entirely out of range returned at the top)
         {
             const long long eps = warp_sum(acc_eps);
@@ -640,14 +699,10 @@ sa_reset_kernel(SaPtrs S, const uint8_t *__restrict__ mask, float *__restrict__ 
     if (mask && !mask[i]) return;
     SaEnv e;
     sa_reset_env(e);
-    sa_store(e, S, i, n);
+    sa_store(e, S, i);
     S.stat[i] = make_uint4(0u, S.stat[i].y, 0u, 0u);  // spawn_ctr survives so that every episode sees fresh obstacles
     if (obs) {
-        float2 row[9];
-        sa_observe<false>(e, row);
-        float2 *dst = reinterpret_cast<float2 *>(obs + i * HW_SA_OBS_DIM);
-#pragma unroll
-        for (int j = 0; j < 9; ++j) dst[j] = row[j];
+        sa_observe<false>(e, PtrRow{reinterpret_cast<float2 *>(obs + i * HW_SA_OBS_DIM)});
     }
 }
 
@@ -657,14 +712,14 @@ sa_observe_kernel(SaPtrs S, float *__restrict__ obs, const int64_t n)
     __shared__ __align__(16) float sm_obs[kSaBlock * HW_SA_OBS_DIM];
     const int64_t i = (int64_t)blockIdx.x * kSaBlock + threadIdx.x;
     const int64_t warp_base = i - (threadIdx.x & 31);
-    float *sm_tile = sm_obs + (threadIdx.x >> 5) * 32 * HW_SA_OBS_DIM;
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(sm_obs) + (threadIdx.x >> 5) * (32 * HW_SA_OBS_DIM * 4);
     if (warp_base >= n) return;
     if (i < n) {
         SaEnv e;
-        sa_load(e, S, i, n);
-        sa_observe<false>(e, reinterpret_cast<float2 *>(sm_tile) + (threadIdx.x & 31) * (HW_SA_OBS_DIM / 2));
+        sa_load(e, S, i);
+        sa_observe<false>(e, SmRow{tile_s + (threadIdx.x & 31) * (HW_SA_OBS_DIM * 4)});
     }
-    store_obs_warp(sm_tile, obs, warp_base, n);
+    store_obs_warp(tile_s, obs, warp_base, n);
 }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -676,14 +731,16 @@ static int check_state(const HwSaState *st, int64_t n)
     return 0;
 }
 
-static SaPtrs ptrs(const HwSaState *st)
+// pointers of the environments [i0, n) of a batch of n
+static SaPtrs ptrs(const HwSaState *st, int64_t n, int64_t i0 = 0)
 {
     SaPtrs S;
-    S.car_a = reinterpret_cast<float4 *>(st->car_a);
-    S.car_b = reinterpret_cast<float4 *>(st->car_b);
-    S.obst = reinterpret_cast<float4 *>(st->obst);
-    S.stat = reinterpret_cast<uint4 *>(st->stat);
-    S.ostride = 0;  // set by the caller
+    S.car_a = reinterpret_cast<float4 *>(st->car_a) + i0;
+    S.car_b = reinterpret_cast<float4 *>(st->car_b) + i0;
+    S.obst0 = reinterpret_cast<float4 *>(st->obst) + i0;
+    S.obst1 = S.obst0 + n;
+    S.obst2 = S.obst1 + n;
+    S.stat = reinterpret_cast<uint4 *>(st->stat) + i0;
     return S;
 }
 
@@ -701,9 +758,8 @@ static int launch_step_range(const HwSaState *st, const void *actions, const HwS
     if (i0 < 0 || count < 1 || i0 + count > n || (i0 & 1)) return HW_E_BADARG;  // an even i0 keeps the observation rows 16-byte aligned
     const bool cont = (flags & HW_FLAG_CONTINUOUS) != 0;
     const bool exact = (flags & HW_FLAG_EXACT_STEERING) != 0;
-    SaPtrs S = ptrs(st);
-    S.ostride = n;
-    S.car_a += i0; S.car_b += i0; S.obst += i0; S.stat += i0;
+    if (count >= ((int64_t)1 << 31)) return HW_E_BADARG;  // environments of one launch are indexed with 32 bits
+    const SaPtrs S = ptrs(st, n, i0);
     const void *act = actions ? static_cast<const char *>(actions) + (size_t)i0 * (cont ? 2 * sizeof(float) : sizeof(int32_t)) : nullptr;
     float *obs = out->obs + i0 * HW_SA_OBS_DIM, *rew = out->rew + i0;
     uint8_t *done = out->done + i0;
@@ -713,6 +769,7 @@ static int launch_step_range(const HwSaState *st, const void *actions, const HwS
     K.k30dt = 30.0 * P->dt;  // python: 30.0 * dt
     K.five_dt = 5.0 + P->dt;
     K.deg2rad = kDeg2Rad;
+    K.respawn_hi = (flags & HW_FLAG_NO_INF_OBS) ? 0xFFFFFFFFu : 0xC0030000u;
     K.rad2deg_q = 0.25 * kRad2Deg;  // exact scaling of the constant
     K.ticks_per_step = P->ticks_per_step;
     K.timeout_tick = P->timeout_tick;
@@ -753,8 +810,8 @@ int hw_sa_reset(const HwSaState *state, const uint8_t *mask, float *obs, int64_t
     int rc = hw::check_state(state, n);
     if (rc) return rc;
     const unsigned grid = (unsigned)((n + hw::kSaBlock - 1) / hw::kSaBlock);
-    hw::SaPtrs S = hw::ptrs(state);
-    S.ostride = n;
+    if (n >= ((int64_t)1 << 31)) return HW_E_BADARG;
+    const hw::SaPtrs S = hw::ptrs(state, n);
     hw::sa_reset_kernel<<<grid, hw::kSaBlock, 0, (cudaStream_t)stream>>>(S, mask, obs, n);
     return (int)cudaGetLastError();
 }
@@ -779,8 +836,8 @@ int hw_sa_observe(const HwSaState *state, float *obs, int64_t n, void *stream)
     if (!obs) return HW_E_BADARG;
     if (!hw::aligned16(obs)) return HW_E_ALIGN;
     const unsigned grid = (unsigned)((n + hw::kSaBlock - 1) / hw::kSaBlock);
-    hw::SaPtrs S = hw::ptrs(state);
-    S.ostride = n;
+    if (n >= ((int64_t)1 << 31)) return HW_E_BADARG;
+    const hw::SaPtrs S = hw::ptrs(state, n);
     hw::sa_observe_kernel<<<grid, hw::kSaBlock, 0, (cudaStream_t)stream>>>(S, obs, n);
     return (int)cudaGetLastError();
 }
