@@ -162,9 +162,8 @@ __device__ __forceinline__ void sa_respawn(SaEnv &e, const uint32_t kNeg, const 
 template <bool CONT, bool FIRST, bool EXACT>
 __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaConsts &K, const bool inf_obs,
                                        const uint32_t amask, const uint32_t apair, const double a0_5dt, const double a1_30dt,
-                                       const uint64_t seed, const uint64_t env_id)
+                                       const uint64_t seed, const uint64_t env_id, const double dt)
 {
-    const double dt = K.dt;
     const bool lock = FIRST && (e.bits & HW_BITS_TICK_MASK) == 0;  // collision_count_lock: first tick after reset
     const double px = FIRST ? e.px : 10.0;
     uint32_t b = e.bits + 1;  // tick field lives in the low 16 bits; 2160 (or 3601) never carries out
@@ -302,12 +301,13 @@ __device__ __forceinline__ int sa_tick(SaEnv &e, uint32_t &ncoll_acc, const SaCo
 //   * the action of the step has fired on its first tick, so it can only fire again after the simulator
 //     cleared the mode it asks for (lane reached, maintain snapped): that whole stage sits behind a branch;
 //   * signs and "< 10.0" are read from the hi words (integer pipe) instead of fp64 compares.
+//   * a collision ends the step after this tick (highway_env.py:99-108): the rare branch that finds one also sets the loop's
+//     `remaining` tick count to 1, so the loop test is one decrement and one compare and knows nothing about collisions.
 template <bool EXACT>
-__device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncoll_acc, const SaConsts &K, const bool inf_obs,
+__device__ __forceinline__ void sa_tick_later(SaEnv &e, int &lane, int &ncol, int &remaining, uint32_t &ncoll_acc, const SaConsts &K, const bool inf_obs,
                                              const uint32_t amask, const uint32_t apair, const int dlane,
-                                             const uint64_t seed, const uint64_t env_id)
+                                             const uint64_t seed, const uint64_t env_id, const double dt)
 {
-    const double dt = K.dt;
     uint32_t b = e.bits + 1;
 
     // ---- apply action (multi_lane_sim.py:502-517, :529-572) ----
@@ -337,7 +337,6 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
     // second tick some lane of a warp passes it (obstacles in the other lanes drift past the car all the time), so
     // the exact test behind it is kept short: the y overlap of rect k (y = 21 + 80k, height 38) with the car's rect
     // is |ay - by| <= 37.
-    int ncol = 0;
     {
         constexpr uint32_t kLo = 0x401EA000u, kSpan = 0x4028C000u - 0x401EA000u;  // hi(7.65625), hi(12.375)
         const bool n0 = hi32(e.opx[0]) - kLo <= kSpan, n1 = hi32(e.opx[1]) - kLo <= kSpan, n2 = hi32(e.opx[2]) - kLo <= kSpan;
@@ -347,8 +346,9 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
             const int u = rect_y(e.py) + 16;                        // window k is u in [80k, 80k + 74]
             const int k = (int)(((uint32_t)u * 205u) >> 14);        // u / 80 for 0 <= u < 240
             const double ox = dsel3(k + 1, e.opx[0], e.opx[1], e.opx[2]);
-            ncol = ((uint32_t)u < 240u) & ((uint32_t)(u - 80 * k) <= 74u) & (ox >= 7.65625) & (ox < 12.375);
-            ncoll_acc += ncol;
+            if (((uint32_t)u < 240u) & ((uint32_t)(u - 80 * k) <= 74u) & (ox >= 7.65625) & (ox < 12.375)) {
+                ncol = 1; remaining = 1; ncoll_acc += 1;
+            }
         }
     }
 
@@ -383,7 +383,8 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
         double sc = e.steer;
         dmov_if(30.0 < fabs(e.steer), sc, copysign(30.0, e.steer));
         // +30*dt in left mode, -30*dt in right mode: the right-mode bit (bit 19) moved onto the sign bit of the increment
-        const double inc = __hiloint2double(__double2hiint(K.k30dt) ^ (int)((b << 12) & 0x80000000u), __double2loint(K.k30dt));
+        const double k30 = K.k30dt;
+        const double inc = __hiloint2double(__double2hiint(k30) ^ (int)((b << 12) & 0x80000000u), __double2loint(k30));
         double st = dadd(sc, inc);
         const double ty = __hiloint2double(l1 ? 0x3FF40000 : (l2 ? 0x400E0000 : 0x40190000), 0);  // 1.25, 3.75, 6.25
         int reached_i;  // (left_mode and y <= target) or (right_mode and y >= target): two compares and one predicate op
@@ -412,7 +413,6 @@ __device__ __forceinline__ int sa_tick_later(SaEnv &e, int &lane, uint32_t &ncol
 
     // ---- respawn (:963-991) ----
     sa_respawn(e, K.respawn_hi, l1, l2, seed, env_id);
-    return ncol;
 }
 
 // velocities of the obstacles after their last update, materialised for the observation and the stored state
@@ -544,7 +544,11 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
     if (warp_base >= n) return;  // whole warp out of range
     const bool inf_obs = !(flags & HW_FLAG_NO_INF_OBS);
     const bool autoreset = !(flags & HW_FLAG_NO_AUTORESET);
-    const double dt = K.dt;
+    // dt is used by a dozen instructions of every tick.  Left to itself ptxas re-loads it from the constant bank at the top of
+    // every tick (LDC.64 + a scoreboard wait in front of the first multiply: 2.8 % of the step, measured); xor-ing the high
+    // word with blockIdx.y (always 0) makes it a value that cannot be rematerialised, so it stays in a register pair.
+    // (Doing the same for 30*dt and 5+dt costs more in registers than the loads it saves: 288.8 us against 280.7 us.)
+    const double dt = __hiloint2double(__double2hiint(K.dt) ^ (int)blockIdx.y, __double2loint(K.dt));
     long long acc_eps = 0, acc_len = 0, acc_ret = 0, acc_col = 0, acc_to = 0;  // finished episodes of this thread
 
     if (i < n) {
@@ -595,16 +599,16 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                 apair = valid ? ((kBitLeft | kBitRight) << (act_d & 2)) : 0u;
             }
             // env.step: up to ticks_per_step ticks, stop at the first crash (highway_env.py:99-108)
-            int ncol = sa_tick<CONT, true, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
+            int ncol = sa_tick<CONT, true, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id, dt);
             e.px = 10.0;  // the only car is always the leader (:212-213)
             if (CONT) {
                 for (int t = 1; t < K.ticks_per_step && ncol == 0; ++t)
-                    ncol = sa_tick<CONT, false, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id);
+                    ncol = sa_tick<CONT, false, EXACT>(e, ncoll_step, K, inf_obs, amask, apair, a0_5dt, a1_30dt, seed, env_id, dt);
             } else {
                 int lane = (int)((e.bits >> HW_BITS_LANE_SHIFT) & 3u);
                 const int dlane = ((uint32_t)act_d < 2u) ? 2 * act_d - 1 : 0;  // LEFT -1, RIGHT +1
-                for (int t = 1; t < K.ticks_per_step && ncol == 0; ++t)
-                    ncol = sa_tick_later<EXACT>(e, lane, ncoll_step, K, inf_obs, amask, apair, dlane, seed, env_id);
+                for (int remaining = (ncol == 0) ? K.ticks_per_step - 1 : 0; remaining > 0; --remaining)
+                    sa_tick_later<EXACT>(e, lane, ncol, remaining, ncoll_step, K, inf_obs, amask, apair, dlane, seed, env_id, dt);
                 e.bits = (e.bits & ~(3u << HW_BITS_LANE_SHIFT)) | ((uint32_t)lane << HW_BITS_LANE_SHIFT);
             }
             const uint32_t tick = e.bits & HW_BITS_TICK_MASK;
