@@ -8,26 +8,4 @@ from . import spaces, utils, error  # noqa: F401
 from . import envs  # noqa: F401
 
 
-class Env(object):
-    metadata = {}
-    reward_range = (-float("inf"), float("inf"))
-    spec = None
-    action_space = None
-    observation_space = None
-
-    @property
-    def unwrapped(self):
-        return self
-
-    def close(self):
-        return None
-
-    def seed(self, seed=None):
-        return []
-
-
-class Wrapper(Env):
-    def __init__(self, env):
-        self.env = env
-        self.action_space = env.action_space
-        self.observation_space = env.observation_space
+from .core import Env, Wrapper  # noqa: F401,E402
