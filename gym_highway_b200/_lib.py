@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhighway_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 FLAG_CONTINUOUS = 1
 FLAG_NO_INF_OBS = 2
@@ -46,6 +46,22 @@ class HwMaOut(C.Structure):
                 ("stats", C.c_void_p)]
 
 
+class HwRing(C.Structure):
+    _fields_ = [("obs0", C.c_void_p), ("obs1", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p),
+                ("terminals1", C.c_void_p), ("state", C.c_void_p)]
+
+
+class HwTransitionBlock(C.Structure):
+    _fields_ = [("obs0", C.c_void_p), ("stride_obs0", C.c_int64), ("obs1", C.c_void_p), ("stride_obs1", C.c_int64),
+                ("actions", C.c_void_p), ("stride_actions", C.c_int64), ("rewards", C.c_void_p), ("stride_rewards", C.c_int64),
+                ("done", C.c_void_p), ("stride_done", C.c_int64), ("done_is_float", C.c_int32)]
+
+
+class HwEpisodeTracker(C.Structure):
+    _fields_ = [("ep_reward", C.c_void_p), ("ep_step", C.c_void_p), ("fin_reward", C.c_void_p), ("fin_step", C.c_void_p),
+                ("epoch_reward", C.c_void_p), ("epoch_counts", C.c_void_p)]
+
+
 class HighwayLibraryError(RuntimeError):
     pass
 
@@ -69,7 +85,12 @@ _EXPORTS = {
                                   C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
     "hw_policy_sample_gaussian2": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "hw_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+    "hw_ring_store": (C.c_int, [C.POINTER(HwRing), C.POINTER(HwTransitionBlock), C.POINTER(HwEpisodeTracker), C.c_int64, C.c_int,
+                                C.c_int, C.c_int, C.c_int64, C.c_float, C.c_void_p]),
+    "hw_obs_moments_workspace": (C.c_int64, [C.c_int64, C.c_int]),
+    "hw_obs_moments": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hw_nstep_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    "hw_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int,
                          C.c_int64, C.c_void_p]),
     "hw_cast_pad_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "hw_policy_sample_discrete": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p,

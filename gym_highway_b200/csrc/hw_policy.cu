@@ -112,29 +112,63 @@ policy_sample_gaussian2_kernel(const T *__restrict__ head, const int stride, con
 //   delta = r[t] + gamma * V[t+1] * (1 - dones[t+1]) - V[t];  A[t] = delta + gamma * lam * (1 - dones[t+1]) * A[t+1]
 __global__ void __launch_bounds__(256)
 gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values, const uint8_t *__restrict__ dones,
-           const float *__restrict__ last_values, const float gamma, const float lam, float *__restrict__ returns,
+           const float *__restrict__ last_values, const double gamma, const double lam, float *__restrict__ returns,
            float *__restrict__ advantages, const int T, const int64_t n)
 {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    float nextvalue = last_values[i], lastgaelam = 0.f;
-    float nextnonterminal = 1.0f - (float)dones[(int64_t)T * n + i];
+    // The precisions of the runner's NumPy expressions, operation by operation (ppo2/runner.py:57-65): rewards and values are
+    // float32 arrays, `1.0 - dones` is float64, so `gamma * nextvalues` is a float32 product (the Python scalar adopts the
+    // array's type) and everything after it float64; lastgaelam stays float64 across steps, mb_advs[t] is its float32
+    // rounding, and mb_returns = mb_advs + mb_values is a float32 sum.
+    const float g32 = (float)gamma;
+    const double gl = gamma * lam;
+    float nextvalue = last_values[i];
+    double lastgaelam = 0.0;
+    double nextnonterminal = 1.0 - (double)dones[(int64_t)T * n + i];
     for (int t = T - 1; t >= 0; --t) {
         const float v = values[(int64_t)t * n + i];
-        // the same association order as the runner's numpy expressions (float32 throughout)
-        const float delta = __fsub_rn(__fadd_rn(rewards[(int64_t)t * n + i], __fmul_rn(__fmul_rn(gamma, nextvalue), nextnonterminal)), v);
-        lastgaelam = __fadd_rn(delta, __fmul_rn(__fmul_rn(__fmul_rn(gamma, lam), nextnonterminal), lastgaelam));
-        if (advantages) advantages[(int64_t)t * n + i] = lastgaelam;
-        returns[(int64_t)t * n + i] = __fadd_rn(lastgaelam, v);
+        const double delta = __dsub_rn(__dadd_rn((double)rewards[(int64_t)t * n + i], __dmul_rn((double)__fmul_rn(g32, nextvalue), nextnonterminal)), (double)v);
+        lastgaelam = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, nextnonterminal), lastgaelam));
+        const float adv = (float)lastgaelam;
+        if (advantages) advantages[(int64_t)t * n + i] = adv;
+        returns[(int64_t)t * n + i] = __fadd_rn(adv, v);
         nextvalue = v;
-        nextnonterminal = 1.0f - (float)dones[(int64_t)t * n + i];
+        nextnonterminal = 1.0 - (double)dones[(int64_t)t * n + i];
+    }
+}
+
+// n-step discounted returns of a2c's runner (baselines/a2c/runner.py:55-66 with a2c/utils.py:147-153 discount_with_dones):
+// per env, r = reward + gamma * r * (1. - done) walked backwards over Python floats (float64) - the float32 rewards, and
+// the float32 bootstrap value appended as one more "reward" when the last step did not end the episode - then stored
+// back into the float32 reward row.  dones: uint8 [T + 1][n] with row t + 1 = the episode ended ON step t (row 0 unused).
+__global__ void __launch_bounds__(256)
+nstep_returns_kernel(const float *__restrict__ rewards, const uint8_t *__restrict__ dones, const float *__restrict__ last_values,
+                     const double gamma, float *__restrict__ out, const int T, const int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    // dones[-1] == 0: discount_with_dones(rewards + [value], dones + [0]) starts from r = value + gamma * 0 * 1 = value
+    double r = dones[(int64_t)T * n + i] ? 0.0 : __dadd_rn((double)last_values[i], __dmul_rn(__dmul_rn(gamma, 0.0), 1.0));
+    for (int t = T - 1; t >= 0; --t) {
+        const double nd = 1.0 - (double)dones[(int64_t)(t + 1) * n + i];
+        r = __dadd_rn((double)rewards[(int64_t)t * n + i], __dmul_rn(__dmul_rn(gamma, r), nd));
+        out[(int64_t)t * n + i] = (float)r;
     }
 }
 
 }  // namespace hw
 
-extern "C" int hw_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_values, float gamma,
-                      float lam, float *returns, float *advantages, int T, int64_t n, void *stream)
+extern "C" int hw_nstep_returns(const float *rewards, const uint8_t *dones, const float *last_values, double gamma, float *out, int T,
+                                int64_t n, void *stream)
+{
+    if (!rewards || !dones || !last_values || !out || T < 1 || n <= 0) return HW_E_BADARG;
+    hw::nstep_returns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, dones, last_values, gamma, out, T, n);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int hw_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_values, double gamma,
+                      double lam, float *returns, float *advantages, int T, int64_t n, void *stream)
 {
     if (!rewards || !values || !dones || !last_values || !returns || T < 1 || n <= 0) return HW_E_BADARG;
     hw::gae_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, gamma, lam, returns,

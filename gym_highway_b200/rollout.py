@@ -145,35 +145,41 @@ class MlpPolicy(nn.Module):
 
 
 def gae(rewards, values, dones, last_values, last_dones, gamma, lam):
-    """Generalised advantage estimation exactly as ppo2's runner computes it (runner.py:53-65).
+    """Generalised advantage estimation exactly as ppo2's runner computes it (runner.py:53-65), precision by precision:
+    `gamma * nextvalues` is a float32 product, `1.0 - dones` makes everything after it float64, lastgaelam is carried in
+    float64, the stored advantage is its float32 rounding and returns = advantages + values is a float32 sum.
     rewards, values: [T, N]; dones[t] = the `self.dones` the runner stored at step t, i.e. whether the episode
     ended on the transition BEFORE step t; last_dones = dones after the final step.  Returns (returns, advantages)."""
     T = rewards.shape[0]
     adv = torch.zeros_like(rewards)
-    lastgaelam = torch.zeros_like(last_values)
+    lastgaelam = torch.zeros_like(last_values, dtype=torch.float64)
+    g32 = torch.tensor(gamma, dtype=torch.float32, device=rewards.device)
+    gl = float(gamma) * float(lam)
     for t in reversed(range(T)):
         if t == T - 1:
-            nextnonterminal = 1.0 - last_dones
+            nextnonterminal = 1.0 - last_dones.to(torch.float64)
             nextvalues = last_values
         else:
-            nextnonterminal = 1.0 - dones[t + 1]
+            nextnonterminal = 1.0 - dones[t + 1].to(torch.float64)
             nextvalues = values[t + 1]
-        delta = rewards[t] + gamma * nextvalues * nextnonterminal - values[t]
-        lastgaelam = delta + gamma * lam * nextnonterminal * lastgaelam
-        adv[t] = lastgaelam
+        delta = rewards[t].to(torch.float64) + (g32 * nextvalues).to(torch.float64) * nextnonterminal - values[t].to(torch.float64)
+        lastgaelam = delta + gl * nextnonterminal * lastgaelam
+        adv[t] = lastgaelam.to(torch.float32)
     return adv + values, adv
 
 
 def discount_with_dones(rewards, dones, gamma, bootstrap=None):
-    """n-step discounted returns of a2c's runner (a2c/utils.py discount_with_dones, a2c/runner.py:55-66).
-    rewards, dones: [T, N] with dones[t] = episode ended ON step t; bootstrap: value of the state after the last step
-    (used where the last step did not end the episode)."""
+    """n-step discounted returns of a2c's runner (a2c/utils.py:147-153 discount_with_dones, a2c/runner.py:55-66): the
+    recursion runs over Python floats there, i.e. in float64 on the float32 rewards / bootstrap values, and the result is
+    stored back as float32.  rewards, dones: [T, N] with dones[t] = episode ended ON step t; bootstrap: value of the state
+    after the last step (used where the last step did not end the episode)."""
     T = rewards.shape[0]
     out = torch.zeros_like(rewards)
-    r = torch.zeros_like(rewards[0]) if bootstrap is None else bootstrap * (1.0 - dones[-1])
+    nd = 1.0 - dones.to(torch.float64)
+    r = torch.zeros_like(rewards[0], dtype=torch.float64) if bootstrap is None else bootstrap.to(torch.float64) * nd[-1]
     for t in reversed(range(T)):
-        r = rewards[t] + gamma * r * (1.0 - dones[t])
-        out[t] = r
+        r = rewards[t].to(torch.float64) + (gamma * r) * nd[t]
+        out[t] = r.to(torch.float32)
     return out
 
 
@@ -295,27 +301,31 @@ class A2CRunner(object):
         return sf01(self.mb_obs), None, sf01(rewards), sf01(masks), sf01(self.mb_actions), sf01(self.mb_values)
 
 
-class DeviceRunner(object):
-    """ppo2's Runner (baselines/ppo2/runner.py:20-66) for a `HighwayVecEnv` (discrete or continuous), with nothing between the policy's
-    GEMMs and the env kernel but ONE launch: `hw_policy_sample_discrete` / `hw_policy_sample_gaussian2` turns the merged head's output into actions, values
-    and neglogpacs written in place into the rollout's [T, N] buffers, and the env step writes the next observation, the
-    reward and the done flag straight into theirs (`step_into`) - no per-step copies, casts or elementwise torch kernels.
-    `run()` returns what `Runner.run(want_epinfos=False)` returns; `run_graphed()` replays the rollout from one CUDA graph.
-    Actions are sampled from a Philox stream keyed by (seed, global env id, step counter), so a rollout is reproducible
-    and independent of how the envs are sharded over GPUs."""
+class _DeviceCollector(object):
+    """what the on-device runners share: [T, rows] rollout buffers the kernels write in place, the fused sampling launch, and
+    CUDA-graph capture of a whole rollout.  `rows` = num_envs for the single-agent env and num_envs * A for the multi-agent
+    env (every car is one row of the shared policy's batch: observations [N, A, 4A+14] are [N * A, 4A+14] rows in memory,
+    rewards / dones [N, A] are [N * A])."""
 
-    def __init__(self, env, model, nsteps, gamma=0.99, lam=0.95, seed=0):
+    def __init__(self, env, model, nsteps, seed):
         self.continuous = bool(getattr(env, "continuous", False))
         if self.continuous != bool(model.continuous):
             raise ValueError("policy and env disagree on the action space")
         from . import _lib
         self._libmod, self._lib = _lib, _lib.load()
-        self.env, self.model, self.nsteps, self.gamma, self.lam = env, model, nsteps, gamma, lam
+        self.env, self.model, self.nsteps = env, model, nsteps
         self.seed = int(seed) & (2 ** 64 - 1)
-        n, dev = env.num_envs, env.device
+        self.agents = int(getattr(env, "num_agents", 0))          # 0: single-agent env
+        A = max(self.agents, 1)
+        self.rows = env.num_envs * A
+        self.row_id0 = env._env_id0 * A                           # global row id of this shard's first row (Philox key)
+        self.obs_dim = int(env.obs_dim) if self.agents else 18
+        if model.body[0].in_features != self.obs_dim:
+            raise ValueError("the policy reads %d inputs, the env observes %d" % (model.body[0].in_features, self.obs_dim))
+        n, dev = self.rows, env.device
         self.n_actions = model.pi.out_features
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)   # steps sampled so far (device side: survives graph replay)
-        self.mb_obs = torch.empty(nsteps + 1, n, 18, dtype=torch.float32, device=dev)   # row t: what the policy saw at step t
+        self.mb_obs = torch.empty(nsteps + 1, n, self.obs_dim, dtype=torch.float32, device=dev)   # row t: what the policy saw at step t
         self.mb_done_u8 = torch.zeros(nsteps + 1, n, dtype=torch.uint8, device=dev)      # row t: episode ended BEFORE step t
         self.mb_rewards = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
         self.mb_actions = (torch.empty(nsteps, n, 2, dtype=torch.float32, device=dev) if self.continuous
@@ -323,29 +333,32 @@ class DeviceRunner(object):
         self.env_actions = torch.empty(n, 2, dtype=torch.float32, device=dev) if self.continuous else None  # clamped to [-1, 1]
         self.mb_values = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
         self.mb_neglogpacs = torch.empty(nsteps, n, dtype=torch.float32, device=dev)
-        self.mb_obs[nsteps].copy_(env.reset())
+        self.mb_obs[nsteps].copy_(env.reset().reshape(n, self.obs_dim))
         self._graph = None
+
+    def _stream(self):
+        import ctypes as C
+        return C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
 
     def _sample(self, head, t):
         import ctypes as C
         p = lambda x: C.c_void_p(x.data_ptr())
-        stream = C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
         bf16 = 1 if head.dtype == torch.bfloat16 else 0
         with torch.cuda.device(self.env.device):
             if self.continuous:
                 rc = self._lib.hw_policy_sample_gaussian2(p(head), bf16, head.shape[1], p(self.model.logstd.detach()), self.seed,
-                                                          self.env._env_id0, t, p(self.step_counter), p(self.mb_actions[t]),
+                                                          self.row_id0, t, p(self.step_counter), p(self.mb_actions[t]),
                                                           p(self.env_actions), p(self.mb_neglogpacs[t]), p(self.mb_values[t]),
-                                                          head.shape[0], stream)
+                                                          head.shape[0], self._stream())
             else:
-                rc = self._lib.hw_policy_sample_discrete(p(head), bf16, head.shape[1], self.n_actions, self.seed, self.env._env_id0, t,
+                rc = self._lib.hw_policy_sample_discrete(p(head), bf16, head.shape[1], self.n_actions, self.seed, self.row_id0, t,
                                                          p(self.step_counter), p(self.mb_actions[t]), p(self.mb_neglogpacs[t]),
-                                                         p(self.mb_values[t]), head.shape[0], stream)
+                                                         p(self.mb_values[t]), head.shape[0], self._stream())
         self._libmod.check(rc, "hw_policy_sample")
         return self.env_actions if self.continuous else self.mb_actions[t]
 
-    @torch.no_grad()
-    def run(self):
+    def _collect(self):
+        """T x (policy forward, one sampling launch, one env step writing obs / reward / done into row t + 1 / t / t + 1)"""
         T = self.nsteps
         self.model.refresh_bf16_()  # bf16 weight copies re-cast in place: part of the captured graph, so replays see optimizer steps
         # the last observation / done row of the previous rollout is the first of this one
@@ -355,19 +368,6 @@ class DeviceRunner(object):
             act = self._sample(self.model.head_bf16(self.mb_obs[t]), t)
             self.env.step_into(act, self.mb_obs[t + 1], self.mb_rewards[t], self.mb_done_u8[t + 1])
         self.step_counter += T
-        dones = self.mb_done_u8.to(torch.float32)
-        last_values = self.model.value(self.mb_obs[T]).contiguous()
-        # GAE in one launch (the torch loop is 8 small kernels per step: a fifth of the rollout at T = 240)
-        import ctypes as C
-        returns = torch.empty_like(self.mb_rewards)
-        with torch.cuda.device(self.env.device):
-            rc = self._lib.hw_gae(C.c_void_p(self.mb_rewards.data_ptr()), C.c_void_p(self.mb_values.data_ptr()),
-                                  C.c_void_p(self.mb_done_u8.data_ptr()), C.c_void_p(last_values.data_ptr()), self.gamma, self.lam,
-                                  C.c_void_p(returns.data_ptr()), None, T, self.env.num_envs,
-                                  C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream))
-        self._libmod.check(rc, "hw_gae")
-        return (sf01(self.mb_obs[:T]), sf01(returns), sf01(dones[:T]), sf01(self.mb_actions), sf01(self.mb_values),
-                sf01(self.mb_neglogpacs), None, [])
 
     @torch.no_grad()
     def run_graphed(self):
@@ -378,6 +378,68 @@ class DeviceRunner(object):
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
-                self._g_out = self.run()[:7]
+                self._g_out = self.run()
         self._graph.replay()
-        return self._g_out + ([],)
+        return self._g_out
+
+
+class DeviceRunner(_DeviceCollector):
+    """ppo2's Runner (baselines/ppo2/runner.py:20-66) for a `HighwayVecEnv` or a `HighwayMAVecEnv` (discrete or continuous), with
+    nothing between the policy's GEMMs and the env kernel but ONE launch: `hw_policy_sample_discrete` /
+    `hw_policy_sample_gaussian2` turns the merged head's output into actions, values and neglogpacs written in place into the
+    rollout's [T, rows] buffers, and the env step writes the next observation, the reward and the done flag straight into
+    theirs (`step_into`) - no per-step copies, casts or elementwise torch kernels.  `run()` returns what
+    `Runner.run(want_epinfos=False)` returns; `run_graphed()` replays the rollout from one CUDA graph.
+    Actions are sampled from a Philox stream keyed by (seed, global row id, step counter), so a rollout is reproducible
+    and independent of how the envs are sharded over GPUs.  For the multi-agent env every car is a row of the batch (the
+    cars share the policy; a row's done flag is its own car's, and all cars of an env restart together when any of them
+    finishes, dummy_vec_ma_env.py:74-77)."""
+
+    def __init__(self, env, model, nsteps, gamma=0.99, lam=0.95, seed=0):
+        _DeviceCollector.__init__(self, env, model, nsteps, seed)
+        self.gamma, self.lam = gamma, lam
+
+    @torch.no_grad()
+    def run(self):
+        T = self.nsteps
+        self._collect()
+        dones = self.mb_done_u8.to(torch.float32)
+        last_values = self.model.value(self.mb_obs[T]).contiguous()
+        # GAE in one launch (the torch loop is 8 small kernels per step: a fifth of the rollout at T = 240)
+        import ctypes as C
+        returns = torch.empty_like(self.mb_rewards)
+        with torch.cuda.device(self.env.device):
+            rc = self._lib.hw_gae(C.c_void_p(self.mb_rewards.data_ptr()), C.c_void_p(self.mb_values.data_ptr()),
+                                  C.c_void_p(self.mb_done_u8.data_ptr()), C.c_void_p(last_values.data_ptr()), self.gamma, self.lam,
+                                  C.c_void_p(returns.data_ptr()), None, T, self.rows, self._stream())
+        self._libmod.check(rc, "hw_gae")
+        return (sf01(self.mb_obs[:T]), sf01(returns), sf01(dones[:T]), sf01(self.mb_actions), sf01(self.mb_values),
+                sf01(self.mb_neglogpacs), None, [])
+
+
+class DeviceA2CRunner(_DeviceCollector):
+    """a2c's Runner (baselines/a2c/runner.py:21-72) on the device path of `DeviceRunner`: fused sampling, `step_into`, and the
+    n-step discounted returns with value bootstrap in one launch (`hw_nstep_returns`: discount_with_dones, a2c/utils.py:147-153,
+    in the float64 of the reference's Python floats); `run_graphed()` replays the nsteps (5 by default) from one CUDA graph.
+    `run()` returns (obs, states, rewards, masks, actions, values) flattened environment-major like the reference."""
+
+    def __init__(self, env, model, nsteps=5, gamma=0.99, seed=0):
+        _DeviceCollector.__init__(self, env, model, nsteps, seed)
+        self.gamma = gamma
+
+    @torch.no_grad()
+    def run(self):
+        T = self.nsteps
+        self._collect()
+        rewards = self.mb_rewards
+        if self.gamma > 0.0:
+            import ctypes as C
+            last_values = self.model.value(self.mb_obs[T]).contiguous()
+            rewards = torch.empty_like(self.mb_rewards)
+            with torch.cuda.device(self.env.device):
+                rc = self._lib.hw_nstep_returns(C.c_void_p(self.mb_rewards.data_ptr()), C.c_void_p(self.mb_done_u8.data_ptr()),
+                                                C.c_void_p(last_values.data_ptr()), self.gamma, C.c_void_p(rewards.data_ptr()), T,
+                                                self.rows, self._stream())
+            self._libmod.check(rc, "hw_nstep_returns")
+        masks = self.mb_done_u8[:T].to(torch.float32)
+        return sf01(self.mb_obs[:T]), None, sf01(rewards), sf01(masks), sf01(self.mb_actions), sf01(self.mb_values)

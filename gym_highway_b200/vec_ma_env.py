@@ -154,6 +154,20 @@ class HighwayMAVecEnv(VecEnv):
         infos = LazyInfos(self.num_envs, self._make_info_fetcher(out))
         return self._wrap(out['obs']), self._wrap(out['rew']), self._wrap(out['done'], True), infos
 
+    def step_into(self, actions, obs, rew, done):
+        """step() with caller-provided output tensors (float32 [N, A, 4A+14], float32 [N, A], uint8 [N, A] on this device,
+        contiguous): the kernel writes straight into them - e.g. rows of a rollout's [T, N, A] buffers.  `actions` must
+        already be an int32 [N, A] (float32 [N, A, 2] when continuous) tensor on this device.  Asynchronous; no infos
+        (use episode_statistics())."""
+        assert not self.closed and self._pending is None
+        self._serial += 1
+        out = _lib.HwMaOut(obs.data_ptr(), rew.data_ptr(), done.data_ptr(), self._out[0]['term'].data_ptr(),
+                           self.stats.data_ptr() if self.stats is not None else 0)
+        with torch.cuda.device(self.device):
+            rc = self._lib.hw_ma_step(C.byref(self._state_c), _as_ptr(actions), C.byref(out), C.byref(self.params),
+                                      self._seed, self._env_id0, self.num_envs, self._flags, self._stream())
+        _lib.check(rc, "hw_ma_step")
+
     def step_host(self, actions):
         n, A = self.num_envs, self.num_agents
         if self._host is None:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define HW_ABI_VERSION 2
+#define HW_ABI_VERSION 3
 
 #define HW_E_BADARG (-1)   /* null pointer / non-positive size / unsupported combination */
 #define HW_E_ALIGN  (-2)   /* a 16-byte-aligned pointer was required */
@@ -206,14 +206,64 @@ int hw_policy_sample_gaussian2(const void *head, int head_is_bf16, int stride, c
 
 /* GAE(gamma, lam) of ppo2's runner (baselines/ppo2/runner.py:53-65) over step-major [T][n] buffers in one launch:
  * dones is uint8 [T + 1][n] (row t: the episode ended before step t; row T: after the last step), last_values [n] the value
- * of the state after the last step.  Writes returns = advantages + values, and the advantages when `advantages` is non-NULL. */
-int hw_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_values, float gamma, float lam,
+ * of the state after the last step.  Writes returns = advantages + values, and the advantages when `advantages` is non-NULL.
+ * Precisions follow the runner's NumPy expressions: float32 gamma * V, float64 recursion, float32 advantages and returns. */
+int hw_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_values, double gamma, double lam,
            float *returns, float *advantages, int T, int64_t n, void *stream);
+
+/* n-step discounted returns of a2c's runner (baselines/a2c/runner.py:55-66, a2c/utils.py:147-153 discount_with_dones) over
+ * step-major [T][n] float32 rewards in one launch: dones is uint8 [T + 1][n] with row t + 1 = the episode ended ON step t
+ * (row 0, "ended before the first step", is not read), last_values [n] bootstraps the envs whose last step did not end an
+ * episode.  The recursion runs in float64 like the reference's Python floats; out [T][n] float32 (may alias rewards). */
+int hw_nstep_returns(const float *rewards, const uint8_t *dones, const float *last_values, double gamma, float *out, int T,
+                     int64_t n, void *stream);
 
 #define HW_POLICY_MAX_ACTIONS 8
 int hw_policy_sample_discrete(const void *head, int head_is_bf16, int stride, int n_actions, uint64_t seed,
                               uint64_t env_id0, uint64_t counter, const unsigned long long *counter_offset,
                               int32_t *actions, float *neglogp, float *values, int64_t n, void *stream);
+
+/* ---- transition store of the MADDPG / DDPG consumers ----
+ * Replaces, per rollout step, the host loops of maddpg/trainer/ma_ddpg.py:228-262 (episode bookkeeping), :233-237 with
+ * ma_ddpg_learner.py:390-396 (store_transition -> Memory.append per env and agent, ma_memory.py:20-31, :74-83) and
+ * baselines/common/mpi_running_mean_std.py:41-48 (the float64 sum / sum of squares / count vector that is all-reduced). */
+typedef struct HwRing {            /* per-agent ring buffers, stored together: row r of agent a at [r][a] */
+    float *obs0;                   /* [limit][A][obs_dim] */
+    float *obs1;                   /* [limit][A][obs_dim] */
+    float *actions;                /* [limit][A][act_dim] */
+    float *rewards;                /* [limit][A]   (already multiplied by reward_scale) */
+    float *terminals1;             /* [limit][A]   0 / 1 */
+    int64_t *state;                /* device words {start, length, appended_total}: RingBuffer.start / .length */
+} HwRing;
+
+typedef struct HwTransitionBlock { /* the (nenvs, A, ...) blocks one env step produced; strides in ELEMENTS between envs */
+    const float *obs0;  int64_t stride_obs0;     /* [n][A][obs_dim]  observation the actions were computed from */
+    const float *obs1;  int64_t stride_obs1;     /* [n][A][obs_dim]  observation the step returned (post-reset where done) */
+    const float *actions; int64_t stride_actions;/* [n][A][act_dim] */
+    const float *rewards; int64_t stride_rewards;/* [n][A] */
+    const void *done;   int64_t stride_done;     /* [n][A] uint8 (env output) or float (done_is_float: a packed, gathered block) */
+    int32_t done_is_float;
+} HwTransitionBlock;
+
+typedef struct HwEpisodeTracker {  /* nullable as a whole, or ep_reward == NULL: no bookkeeping */
+    float *ep_reward;              /* [n][A] running sum of the current episode's rewards (float32, ma_ddpg.py:174) */
+    int64_t *ep_step;              /* [n] */
+    float *fin_reward;             /* [n][A] episode_reward of the envs whose episode ended on this step */
+    int64_t *fin_step;             /* [n]    their episode_step; 0 = the env's episode goes on */
+    double *epoch_reward;          /* [A], nullable: += episode_reward of every finished episode (epoch_episode_rewards) */
+    uint64_t *epoch_counts;        /* [2], nullable: {episodes, sum of episode steps} */
+} HwEpisodeTracker;
+
+/* Append the n transitions of one env step to the ring in env order - what n x A Memory.append calls leave behind (the oldest
+ * entries are overwritten once `limit` is reached; with n > limit only the last `limit` survive) - advance start / length on the
+ * device, and run the episode bookkeeping.  Two launches (store, then a one-thread advance) on `stream`. */
+int hw_ring_store(const HwRing *ring, const HwTransitionBlock *blk, const HwEpisodeTracker *ep, int64_t n, int num_agents,
+                  int obs_dim, int act_dim, int64_t limit, float reward_scale, void *stream);
+
+/* addvec of RunningMeanStd.update for a float32 [n][cols] block: out[0..cols) = column sums, out[cols..2cols) = column sums of
+ * squares (float64, deterministic summation order), out[2*cols] = count.  workspace: hw_obs_moments_workspace(n, cols) bytes. */
+int64_t hw_obs_moments_workspace(int64_t n, int cols);
+int hw_obs_moments(const float *x, int64_t n, int cols, double count, double *workspace, double *out, void *stream);
 
 #ifdef __cplusplus
 }
