@@ -153,7 +153,6 @@ def gae(rewards, values, dones, last_values, last_dones, gamma, lam):
     T = rewards.shape[0]
     adv = torch.zeros_like(rewards)
     lastgaelam = torch.zeros_like(last_values, dtype=torch.float64)
-    g32 = torch.tensor(gamma, dtype=torch.float32, device=rewards.device)
     gl = float(gamma) * float(lam)
     for t in reversed(range(T)):
         if t == T - 1:
@@ -162,7 +161,8 @@ def gae(rewards, values, dones, last_values, last_dones, gamma, lam):
         else:
             nextnonterminal = 1.0 - dones[t + 1].to(torch.float64)
             nextvalues = values[t + 1]
-        delta = rewards[t].to(torch.float64) + (g32 * nextvalues).to(torch.float64) * nextnonterminal - values[t].to(torch.float64)
+        gv = nextvalues * float(gamma)  # a float32 product: the scalar adopts the tensor's type
+        delta = rewards[t].to(torch.float64) + gv.to(torch.float64) * nextnonterminal - values[t].to(torch.float64)
         lastgaelam = delta + gl * nextnonterminal * lastgaelam
         adv[t] = lastgaelam.to(torch.float32)
     return adv + values, adv

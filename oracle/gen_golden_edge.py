@@ -1,0 +1,272 @@
+"""Forced edge-case golden transitions from the UNMODIFIED reference (build container only).
+
+    python -m oracle.gen_golden_edge
+
+Random trajectories (gen_golden.py) reach the rare branches only by luck.  Here each transition starts from a
+hand-constructed, float32-representable state injected into the reference through ref_harness.py, so that the branch in
+question is taken inside the step: lane-edge LEFT / RIGHT, the y clamps, touching versus
+overlapping rects (dx = 76 px, dy = 38 px), the time-out tick, respawn on a chosen tick, and for the multi-agent world
+the phantom default-rect collision (a freshly spawned obstacle still carries pygame's rect (0, 0, 76, 38) in the tick's
+check_collisions, highway_core.py:314-316 then :407), retire-heavy obstacle lists (nobs 6..10, :327-342), car-car
+contact, the time-out that finishes every car (:276-277).  Files have the format of gen_golden.py / gen_golden_ma.py and
+are consumed by the same tests.  TEST INFRASTRUCTURE ONLY.
+"""
+import os
+
+import numpy as np
+
+from . import ma_oracle as mo
+from . import oracle as orc
+from . import ref_harness as rh
+from .gen_golden import GOLDEN_DIR
+
+K = 16
+LEFT, RIGHT, ACC, MAINT = 0, 1, 2, 3
+F_LEFT, F_RIGHT, F_ACC, F_MAINT = 1, 2, 4, 8
+
+
+def _f32(x):
+    return float(np.float32(x))
+
+
+# ------------------------------------------------------------------------------------------------ single agent
+def _sa_case(py=3.75, lane=2, vx=10.0, acc=0.0, steer=0.0, cruise=0.0, flags=0, tick=100, obst=None, ncoll=0, rx=400.0):
+    """car pinned at x = 10 (as after any update); obst = 3 x (px, vx, init_vx) for lanes 1..3, raw x consistent with the frame"""
+    if obst is None:
+        obst = [(40.0, 6.0, 6.0), (55.0, 5.5, 5.5), (70.0, 6.5, 6.5)]
+    car = [10.0, py, rx, vx, acc, steer, cruise]
+    ob = [[o[0], rx + (o[0] - 10.0), o[1], o[2]] for o in obst]
+    return dict(car=[_f32(v) for v in car], lane=lane, flags=flags, tick=tick, obst=[[_f32(v) for v in o] for o in ob], ncoll=ncoll)
+
+
+def sa_cases(continuous):
+    c = []
+    if not continuous:
+        # lane edges: LEFT in lane 1 / RIGHT in lane 3 keep the lane, arm the mode, and the mode ends on the first tick
+        for vx in (0.0, 3.0, 20.0):
+            c.append((_sa_case(py=1.25, lane=1, vx=vx), LEFT))
+            c.append((_sa_case(py=6.25, lane=3, vx=vx), RIGHT))
+            c.append((_sa_case(py=1.25, lane=1, vx=vx, flags=F_RIGHT), LEFT))     # re-arms against a pending RIGHT
+            c.append((_sa_case(py=6.25, lane=3, vx=vx, flags=F_LEFT), RIGHT))
+        # lane 1 + LEFT already armed (the action re-fires nothing), lane change in flight across a step
+        c.append((_sa_case(py=3.2, lane=1, vx=12.0, steer=7.5, flags=F_LEFT), LEFT))
+        c.append((_sa_case(py=4.4, lane=3, vx=12.0, steer=-7.5, flags=F_RIGHT), RIGHT))
+        c.append((_sa_case(py=1.26, lane=1, vx=20.0, steer=25.0, flags=F_LEFT), MAINT))   # reaches y <= 1.25 inside the step
+        # y clamps of update_d (multi_lane_sim.py:219-222): y < 0 -> 0, y > 6 -> min(y, 7); only steering left over without a
+        # mode flag gets the car there
+        for y0, st in ((0.05, 30.0), (0.3, 30.0), (0.0, 12.0), (6.95, -30.0), (6.6, -30.0), (7.0, -12.0), (6.0, -3.0)):
+            c.append((_sa_case(py=y0, lane=1 if y0 < 3 else 3, vx=20.0, steer=st), ACC))
+        # accelerate / maintain corner values: acc < 0 -> 0, acc exactly 5, ceil() ties, cruise from the obstacle ahead
+        c.append((_sa_case(vx=7.0, acc=-2.0, flags=F_ACC), ACC))
+        c.append((_sa_case(vx=7.0, acc=5.0 - 1.0 / 36.0, flags=F_ACC), ACC))
+        c.append((_sa_case(vx=19.99, acc=5.0, flags=F_ACC), ACC))
+        c.append((_sa_case(vx=6.0, cruise=6.0, flags=F_MAINT), MAINT))
+        c.append((_sa_case(vx=5.5, cruise=6.0, flags=F_MAINT), MAINT))
+        c.append((_sa_case(vx=6.0000005, cruise=6.0, flags=F_MAINT), MAINT))
+        c.append((_sa_case(vx=9.0, obst=[(40.0, 6.0, 6.0), (10.0, 5.5, 5.5), (70.0, 6.5, 6.5)]), MAINT))   # same x: not "ahead"
+        c.append((_sa_case(vx=9.0, obst=[(40.0, 6.0, 6.0), (10.000001, 5.5, 5.5), (70.0, 6.5, 6.5)]), MAINT))
+    else:
+        for y0, st in ((1.02, 30.0), (1.0, 5.0), (0.5, 30.0), (6.98, -30.0), (7.0, -5.0), (2.5, 0.0), (5.0, 0.0), (2.4999, 3.0), (5.0001, -3.0)):
+            c.append((_sa_case(py=y0, lane=1 if y0 < 3 else 3, vx=20.0, steer=st), (0.3, 0.0)))
+        c.append((_sa_case(vx=19.9, acc=4.99), (1.0, 1.0)))
+        c.append((_sa_case(vx=0.05, acc=-4.99), (-1.0, -1.0)))
+        c.append((_sa_case(steer=29.9), (0.0, 1.0)))
+        c.append((_sa_case(steer=-29.9), (0.0, -1.0)))
+    act0 = (0.0, 0.0) if continuous else MAINT
+    still = (0.0, 0.0) if continuous else LEFT   # at v = 0 a lane change turns the wheels but moves nothing: rects stay where they are
+    # rect contact in x: the car's rect is at x = 282; an obstacle rect at 282 +- 76 touches, one pixel closer overlaps
+    # (strict inequalities of pygame.Rect.colliderect).  Obstacle lane 2, car in lane 2 (y rect 101 both).
+    for opx in (12.375, 12.40624, 12.3749, 12.34, 7.625, 7.6562, 7.65626, 7.7):
+        c.append((_sa_case(vx=0.0, obst=[(40.0, 6.0, 6.0), (opx, 0.0, 0.0), (70.0, 6.5, 6.5)]), still))
+    # ... and in y: obstacle lane 2 rect y = 101; car rect y = trunc(py * 32 - 19): 63 touches (63 + 38 = 101), 64 overlaps; same below
+    for py in (2.5625, 2.59374, 2.59376, 2.6, 4.9375, 4.90626, 4.90624, 4.9):
+        c.append((_sa_case(py=py, lane=2, vx=0.0, obst=[(40.0, 6.0, 6.0), (10.5, 0.0, 0.0), (70.0, 6.5, 6.5)]), still))
+    # a neighbouring lane's obstacle alongside (cannot overlap: lanes are 80 px apart, rects 38 px high), and an overlap while the
+    # collision lock is still set (tick 0: the first tick does not count it)
+    c.append((_sa_case(py=2.6, lane=2, vx=0.0, obst=[(10.2, 0.0, 0.0), (10.5, 0.0, 0.0), (70.0, 6.5, 6.5)]), act0))
+    c.append((_sa_case(py=3.75, lane=2, vx=0.0, obst=[(40.0, 6.0, 6.0), (10.5, 0.0, 0.0), (70.0, 6.5, 6.5)], tick=0), act0))
+    # time-out: done is evaluated before the update of tick 2160; the nine ticks still run
+    for tk in (2150, 2151, 2152, 2159, 2160):
+        c.append((_sa_case(vx=5.0, tick=tk), act0))
+    # respawn on a chosen tick: an obstacle just ahead of / exactly at / just behind x = -2.375, car faster than it
+    for opx in (-2.375, -2.3750002, -2.2, -1.0):
+        c.append((_sa_case(vx=15.0, obst=[(opx, 5.0, 5.0), (-2.3, 6.0, 6.0), (70.0, 6.5, 6.5)]), act0))
+    # three respawns in one tick (the reset state does that) and the obstacle that yields to the car ahead of it in its lane
+    c.append((_sa_case(vx=20.0, obst=[(-2.38, 5.0, 5.0), (-2.39, 6.0, 6.0), (-2.4, 7.0, 7.0)]), act0))
+    c.append((_sa_case(vx=2.0, obst=[(40.0, 6.0, 6.0), (5.0, 7.0, 7.0), (70.0, 6.5, 6.5)]), act0))
+    c.append((_sa_case(vx=2.0, obst=[(40.0, 6.0, 6.0), (5.0, 1.0, 7.0), (70.0, 6.5, 6.5)]), act0))
+    return c
+
+
+def gen_sa_edge(continuous, seed):
+    ref = rh.RefSingleAgent(continuous=continuous)
+    keys = ("in_car", "in_lane", "in_flags", "in_tick", "in_obst", "in_ncoll", "in_spawn_ctr", "env_id", "action", "out_car", "out_lft",
+            "out_obst", "out_obs", "out_rew", "out_done", "out_ncoll", "out_spawn_ctr")
+    rec = {k: [] for k in keys}
+    for env_id, (case, a) in enumerate(sa_cases(continuous)):
+        st = orc.SaState(1)
+        st.car[0] = case["car"]; st.lane[0] = case["lane"]; st.flags[0] = case["flags"]; st.tick[0] = case["tick"]
+        st.obst[0] = case["obst"]; st.ncoll[0] = case["ncoll"]; st.spawn_ctr[0] = env_id % 3
+        a = np.asarray(a, np.float32) if continuous else int(a)
+        ref.inject(st, 0)
+        prov = rh.PhiloxUniform(seed, env_id, int(st.spawn_ctr[0]))
+        ob, r, d, _ = ref.step(a, prov)
+        nxt = orc.SaState(1)
+        ref.extract(nxt, 0)
+        rec["in_car"].append(st.car[0].copy()); rec["in_lane"].append(st.lane[0]); rec["in_flags"].append(st.flags[0])
+        rec["in_tick"].append(st.tick[0]); rec["in_obst"].append(st.obst[0].copy()); rec["in_ncoll"].append(st.ncoll[0])
+        rec["in_spawn_ctr"].append(st.spawn_ctr[0]); rec["env_id"].append(env_id); rec["action"].append(np.array(a))
+        rec["out_car"].append(nxt.car[0].copy()); rec["out_lft"].append([nxt.lane[0], nxt.flags[0], nxt.tick[0]])
+        rec["out_obst"].append(nxt.obst[0].copy()); rec["out_obs"].append(np.asarray(ob, np.float32))
+        rec["out_rew"].append(float(r)); rec["out_done"].append(bool(d)); rec["out_ncoll"].append(nxt.ncoll[0])
+        rec["out_spawn_ctr"].append(prov.spawn_ctr)
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out.update(seed=np.int64(seed), continuous=np.bool_(continuous), real_time=np.bool_(False), inf_obs=np.bool_(True))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ multi agent
+START5 = [(10.0, 1), (10.0, 3), (7.5, 2), (5.0, 1), (5.0, 3)]
+LC = (1.25, 3.75, 6.25)
+
+
+def _ma_case(A, cars=None, obst=None, tick=100, leader=None, base_rx=500.0, newest=None, fresh=None, nc=(0, 0)):
+    """cars: A x dict(px, lane, py, vx, vy, acc, steer, cruise, flags); obst: list of (px, lane, vx[, init_vx]) in insertion order.
+    raw x = base_rx + (px - 10) for everything (a consistent frame whose leader sits at x = 10)."""
+    cs = []
+    for a in range(A):
+        d = dict(px=START5[a][0], lane=START5[a][1], vx=8.0, vy=0.0, acc=0.0, steer=0.0, cruise=0.0, flags=0)
+        d.update((cars or {}).get(a, {}))
+        d.setdefault("py", LC[d["lane"] - 1])
+        cs.append(d)
+    if obst is None:
+        obst = [(45.0, 1, 6.0), (60.0, 2, 5.5), (75.0, 3, 6.5)]
+    if leader is None:
+        leader = int(np.argmax([c["px"] for c in cs]))
+    if newest is None:
+        newest = [max([k for k, o in enumerate(obst) if o[1] == l + 1], default=-1) for l in range(3)]
+    return dict(cars=cs, obst=obst, tick=tick, leader=leader, base_rx=base_rx, newest=newest, fresh=fresh or [0] * len(obst), nc=nc)
+
+
+def ma_cases(A, continuous):
+    c = []
+    act0 = [(0.0, 0.0)] * A if continuous else [MAINT] * A
+    go = [(1.0, 0.0)] * A if continuous else [ACC] * A
+    # at v = 0 a lane change (or no input) moves nothing: every rect stays where the state put it
+    still = [(0.0, 0.0)] * A if continuous else [RIGHT if START5[a][1] == 3 else LEFT for a in range(A)]
+    last = A - 1
+    # phantom default-rect collision: the lane's newest obstacle falls behind x = -2.375 on tick 1 (leader faster than it), the
+    # spawn's rect is still (0, 0, 76, 38) in this tick's check_collisions, and a trailing lane-1 car whose rect covers the
+    # pixel origin (|rect.x| < 76, rect.y = 21 < 38) is hit by it.  Variants: rect.x = 75 (hit) / 76 (touching: no hit).
+    if A >= 2:
+        for px1, lane1 in ((2.0, 1), (3.53, 1), (3.5625, 1), (3.6, 1), (-1.0, 1), (-1.18, 1), (-1.19, 1), (2.0, 2)):
+            cars = {0: dict(px=10.0, lane=2, vx=12.0), last: dict(px=px1, lane=lane1, vx=12.0)}
+            c.append((_ma_case(A, cars=cars, obst=[(45.0, 1, 6.0), (60.0, 2, 5.5), (-2.37, 3, 5.0)]), act0))
+        # the same with the spawn happening on a later tick of the step, and with two lanes spawning at once
+        cars = {0: dict(px=10.0, lane=2, vx=12.0), last: dict(px=2.0, lane=1, vx=12.0)}
+        c.append((_ma_case(A, cars=cars, obst=[(45.0, 1, 6.0), (60.0, 2, 5.5), (-1.5, 3, 5.0)]), act0))
+        c.append((_ma_case(A, cars=cars, obst=[(-2.36, 1, 6.0), (60.0, 2, 5.5), (-2.37, 3, 5.0)]), act0))
+    # retire-heavy lists: 6..10 live obstacles, several of them about to be cleared by the last car
+    # (threshold: raw x - last.raw x < (-2.375 - leader.x) - 2 = -14.375 with the leader at 10)
+    back = min(START5[a][0] for a in range(A))     # px of the last car
+    thr_px = back - 14.375
+    for extra, v in ((3, 8.0), (5, 8.0), (7, 12.0), (5, 0.5)):
+        obst = [(thr_px + 0.02 * (k + 1) * (1 if k % 2 else -1) - 0.3 * (k // 2), 1 + k % 3, 4.0 + 0.25 * k) for k in range(extra)]
+        obst += [(45.0, 1, 6.0), (60.0, 2, 5.5), (75.0, 3, 6.5)]
+        cars = {a: dict(vx=v) for a in range(A)}
+        c.append((_ma_case(A, cars=cars, obst=obst), go))
+    # two old obstacles exactly at / just inside / just beyond the threshold, nothing moving
+    for d in (0.0, 1e-4, -1e-4):
+        obst = [(thr_px + d, 2, 0.0), (thr_px + d, 1, 0.0), (45.0, 1, 6.0), (60.0, 2, 5.5), (75.0, 3, 6.5)]
+        c.append((_ma_case(A, cars={a: dict(vx=0.0) for a in range(A)}, obst=obst), still))
+    # time-out: every car is done at tick 2160, whatever it does
+    for tk in (2150, 2151, 2152, 2159):
+        c.append((_ma_case(A, tick=tk, cars={a: dict(vx=0.0) for a in range(A)}), act0))
+    # rect contact between cars (same lane: x contact 76 px; neighbouring y: 38 px) and with an obstacle
+    if A >= 4:
+        for px3 in (7.625, 7.6562, 7.65626, 7.7):          # car 3 behind car 0 in lane 1, both standing
+            cars = {a: dict(vx=0.0) for a in range(A)}
+            cars[3] = dict(px=px3, lane=1, vx=0.0)
+            c.append((_ma_case(A, cars=cars), still))
+        for py3 in (2.4375, 2.46874, 2.4374, 2.43):        # car 3 beside car 0's x, drifting into lane 1 from below
+            cars = {a: dict(vx=0.0) for a in range(A)}
+            cars[3] = dict(px=10.0, lane=1, py=py3, vx=0.0)
+            c.append((_ma_case(A, cars=cars), still))
+    for opx in (12.375, 12.3749, 7.625, 7.65626):          # obstacle in lane 1 in front of / behind car 0 (x = 10, lane 1)
+        c.append((_ma_case(A, cars={a: dict(vx=0.0) for a in range(A)}, obst=[(opx, 1, 0.0), (60.0, 2, 5.5), (75.0, 3, 6.5)]), still))
+    # y clamps (lower bound 1 in the multi-agent cars): leftover steering without a mode flag
+    for y0, st in ((1.02, 30.0), (1.0, 10.0), (6.98, -30.0), (7.0, -10.0)):
+        cars = {0: dict(py=y0, lane=1 if y0 < 3 else 3, vx=20.0, steer=st)}
+        c.append((_ma_case(A, cars=cars), go))
+    if not continuous:
+        # lane edges and the order dependence of maintain(): car 1 changes into car 0's lane in the same tick car 0 / car 2 search
+        c.append((_ma_case(A), [LEFT] * A))
+        c.append((_ma_case(A), [RIGHT] * A))
+        if A >= 3:
+            c.append((_ma_case(A, cars={0: dict(px=10.0, lane=1), 1: dict(px=9.0, lane=2), 2: dict(px=4.0, lane=1, vx=3.0)}), [MAINT, LEFT, MAINT] + [ACC] * (A - 3)))
+            c.append((_ma_case(A, cars={0: dict(px=6.0, lane=2, vx=3.0), 1: dict(px=9.0, lane=1), 2: dict(px=10.0, lane=3)}), [MAINT, RIGHT, LEFT] + [MAINT] * (A - 3)))
+    return c
+
+
+def gen_ma_edge(A, continuous, seed):
+    ref = rh.RefMultiAgent(A, continuous=continuous)
+    names = ("in_car", "in_lane", "in_cflags", "in_tick", "in_leader", "in_nobs", "in_obst", "in_olane", "in_ofresh",
+             "in_newest", "in_nc_obs", "in_nc_agent", "in_spawn_ctr", "env_id", "action",
+             "out_car", "out_lane", "out_cflags", "out_tick", "out_leader", "out_nobs", "out_obst", "out_olane", "out_ofresh",
+             "out_newest", "out_nc_obs", "out_nc_agent", "out_spawn_ctr", "out_obs", "out_rew", "out_done")
+    rec = {k: [] for k in names}
+    for env_id, (case, act) in enumerate(ma_cases(A, continuous)):
+        st = mo.MaState(1, A, K)
+        base = case["base_rx"]
+        for a, d in enumerate(case["cars"]):
+            st.car[0, a] = [_f32(v) for v in (d["px"], d["py"], base + (d["px"] - 10.0), d["vx"], d["vy"], d["acc"], d["steer"], d["cruise"])]
+            st.lane[0, a] = d["lane"]; st.cflags[0, a] = d["flags"]
+        st.nobs[0] = len(case["obst"])
+        for k, o in enumerate(case["obst"]):
+            iv = o[3] if len(o) > 3 else o[2]
+            st.obst[0, k] = [_f32(v) for v in (o[0], base + (o[0] - 10.0), o[2], iv)]
+            st.olane[0, k] = o[1]; st.ofresh[0, k] = case["fresh"][k]
+        st.newest[0] = case["newest"]; st.leader[0] = case["leader"]; st.tick[0] = case["tick"]
+        st.nc_obs[0], st.nc_agent[0] = case["nc"]
+        st.spawn_ctr[0] = env_id % 4
+        a = np.asarray(act, np.float32) if continuous else np.asarray(act, np.int64)
+        ref.inject(st, 0)
+        prov = rh.PhiloxUniform(seed, env_id, int(st.spawn_ctr[0]))
+        ob, r, d, _info = ref.step(a, prov)
+        nxt = mo.MaState(1, A, K)
+        ref.extract(nxt, 0)
+        for f in ("car", "lane", "cflags", "tick", "leader", "nobs", "obst", "olane", "ofresh", "newest", "nc_obs", "nc_agent", "spawn_ctr"):
+            rec["in_" + f].append(getattr(st, f)[0].copy())
+        rec["env_id"].append(env_id); rec["action"].append(np.array(a))
+        for f in ("car", "lane", "cflags", "tick", "leader", "nobs", "obst", "olane", "ofresh", "newest", "nc_obs", "nc_agent"):
+            rec["out_" + f].append(getattr(nxt, f)[0].copy())
+        rec["out_spawn_ctr"].append(prov.spawn_ctr)
+        rec["out_obs"].append(np.asarray(ob, np.float64).astype(np.float32))
+        rec["out_rew"].append(np.asarray(r, np.float64)); rec["out_done"].append(np.asarray(d, bool))
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out.update(seed=np.int64(seed), continuous=np.bool_(continuous), real_time=np.bool_(False), inf_obs=np.bool_(True), num_agents=np.int64(A),
+               num_slots=np.int64(K), shared_reward=np.bool_(False))
+    return out
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    jobs = [("sa_discrete_edge", lambda: gen_sa_edge(False, 41)), ("sa_continuous_edge", lambda: gen_sa_edge(True, 42)),
+            ("ma5_discrete_edge", lambda: gen_ma_edge(5, False, 43)), ("ma3_continuous_edge", lambda: gen_ma_edge(3, True, 44)),
+            ("ma2_discrete_edge", lambda: gen_ma_edge(2, False, 45))]
+    for name, fn in jobs:
+        data = fn()
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **data)
+        d = data["out_done"]
+        nd = int(d.sum()) if d.ndim == 1 else int(d.any(axis=-1).sum())
+        extra = ""
+        if "in_nobs" in data:
+            extra = ", nobs in %d..%d -> out %d..%d, agent collisions %d, obstacle collisions %d" % (
+                data["in_nobs"].min(), data["in_nobs"].max(), data["out_nobs"].min(), data["out_nobs"].max(),
+                int(data["out_nc_agent"].sum()), int(data["out_nc_obs"].sum()))
+        print("%-22s %4d transitions, %3d terminal%s" % (name, len(d), nd, extra))
+
+
+if __name__ == "__main__":
+    main()

@@ -9,7 +9,8 @@ from helpers import MA_STATE_FIELDS, bits_equal, f32, load_golden, ma_state_from
 pytestmark = pytest.mark.gpu
 
 MA_GOLDEN = ["ma1_discrete", "ma1_continuous", "ma3_discrete", "ma3_continuous", "ma5_discrete", "ma5_continuous",
-             "ma5_discrete_shared", "ma3_discrete_realtime", "ma3_continuous_noinf"]
+             "ma5_discrete_shared", "ma3_discrete_realtime", "ma3_continuous_noinf",
+             "ma5_discrete_edge", "ma3_continuous_edge", "ma2_discrete_edge"]  # *_edge: forced rare branches (oracle/gen_golden_edge.py)
 
 
 def _env(n, A, **kw):

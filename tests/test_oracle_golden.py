@@ -15,7 +15,7 @@ def test_philox_known_answers_via_spawn_stream():
     assert orc.spawn_uniforms(1, 0, 0) != (u1, u2)
 
 
-@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime", "sa_discrete_noinf"])
+@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime", "sa_discrete_noinf", "sa_discrete_edge", "sa_continuous_edge"])
 def test_sa_oracle_matches_reference_golden(name):
     g = load_golden(name)
     cont, rt, seed = bool(g["continuous"]), bool(g["real_time"]), int(g["seed"])
@@ -78,7 +78,8 @@ def test_sa_threads_and_quantise_are_consistent():
 
 
 MA_GOLDEN = ["ma1_discrete", "ma1_continuous", "ma3_discrete", "ma3_continuous", "ma5_discrete", "ma5_continuous",
-             "ma5_discrete_shared", "ma3_discrete_realtime", "ma3_continuous_noinf"]
+             "ma5_discrete_shared", "ma3_discrete_realtime", "ma3_continuous_noinf",
+             "ma5_discrete_edge", "ma3_continuous_edge", "ma2_discrete_edge"]  # *_edge: forced rare branches (oracle/gen_golden_edge.py)
 
 
 @pytest.mark.parametrize("name", MA_GOLDEN)
@@ -116,3 +117,24 @@ def test_ma_reset_and_threads():
             ob = mo.ma_step(b, act, seed=1, quantise=True, nthreads=4)
             assert bits_equal(oa["obs"], ob["obs"]) and np.array_equal(oa["done"], ob["done"])
         assert bits_equal(a.car, b.car) and a.overflow.max() == 0
+
+
+def test_edge_goldens_contain_the_forced_branches():
+    """oracle/gen_golden_edge.py: the rare branches the files were built for are really in them (reference outputs)"""
+    from helpers import load_golden
+    g = load_golden("ma5_discrete_edge")
+    spawned = g["out_spawn_ctr"].astype(np.int64) - g["in_spawn_ctr"].astype(np.int64)
+    hit_obs = g["out_nc_obs"] - g["in_nc_obs"]
+    one_tick = (g["out_tick"] - g["in_tick"]) == 1
+    # phantom default-rect collision: an obstacle hit on the very tick of a spawn, by a car nowhere near a live obstacle
+    assert int(np.sum((spawned > 0) & (hit_obs > 0) & one_tick)) >= 4
+    assert int(np.sum((spawned > 0) & (hit_obs == 0) & ~g["out_done"].any(axis=1))) >= 2      # rect.x = 76: touching only
+    assert g["in_nobs"].max() == 10 and int(np.sum(g["in_nobs"] - g["out_nobs"] >= 3)) >= 3     # retire-heavy lists
+    assert int(np.sum(g["out_done"].all(axis=1) & (g["out_tick"] == 2160))) >= 3               # time-out finishes every car
+    assert int(np.sum(g["out_nc_agent"] - g["in_nc_agent"] > 0)) >= 4                          # car-car contact
+    s = load_golden("sa_discrete_edge")
+    y = s["out_car"][:, 1]
+    assert (y == 0.0).any() and (y == 7.0).any()                                               # both y clamps of update_d
+    assert int(s["out_done"].sum()) >= 10 and (s["out_lft"][:, 2] == 2160 + 9).any()
+    c = load_golden("sa_continuous_edge")
+    assert (c["out_car"][:, 1] == 1.0).any() and (c["out_car"][:, 1] == 7.0).any()

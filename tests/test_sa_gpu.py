@@ -54,7 +54,7 @@ def test_reset_observation_matches_oracle():
     assert np.array_equal(got.lane, st.lane) and np.array_equal(got.tick, st.tick)
 
 
-@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime", "sa_discrete_noinf"])
+@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime", "sa_discrete_noinf", "sa_discrete_edge", "sa_continuous_edge"])
 def test_golden_transitions(name):
     """reference-recorded transitions: one env per transition, env_id taken from the file"""
     g = load_golden(name)
@@ -256,7 +256,7 @@ def _float_report(name, got, want, max_bitdiff_frac):
     return frac
 
 
-@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime", "sa_discrete_noinf"])
+@pytest.mark.parametrize("name", ["sa_discrete", "sa_continuous", "sa_discrete_realtime", "sa_discrete_noinf", "sa_discrete_edge", "sa_continuous_edge"])
 def test_fast_mode_golden_transitions(name):
     g = load_golden(name)
     n = len(g["out_done"])
