@@ -39,8 +39,14 @@ def _sa_case(py=3.75, lane=2, vx=10.0, acc=0.0, steer=0.0, cruise=0.0, flags=0, 
     return dict(car=[_f32(v) for v in car], lane=lane, flags=flags, tick=tick, obst=[[_f32(v) for v in o] for o in ob], ncoll=ncoll)
 
 
-def sa_cases(continuous):
+def sa_cases(continuous, offmanifold=False):
     c = []
+    if offmanifold:
+        # y clamps of update_d (multi_lane_sim.py:219-222): y < 0 -> 0, y > 6 -> min(y, 7); only steering left over without a
+        # mode flag gets the car there
+        for y0, st in ((0.05, 30.0), (0.3, 30.0), (0.0, 12.0), (6.95, -30.0), (6.6, -30.0), (7.0, -12.0), (6.0, -3.0)):
+            c.append((_sa_case(py=y0, lane=1 if y0 < 3 else 3, vx=20.0, steer=st), ACC))
+        return c
     if not continuous:
         # lane edges: LEFT in lane 1 / RIGHT in lane 3 keep the lane, arm the mode, and the mode ends on the first tick
         for vx in (0.0, 3.0, 20.0):
@@ -52,10 +58,6 @@ def sa_cases(continuous):
         c.append((_sa_case(py=3.2, lane=1, vx=12.0, steer=7.5, flags=F_LEFT), LEFT))
         c.append((_sa_case(py=4.4, lane=3, vx=12.0, steer=-7.5, flags=F_RIGHT), RIGHT))
         c.append((_sa_case(py=1.26, lane=1, vx=20.0, steer=25.0, flags=F_LEFT), MAINT))   # reaches y <= 1.25 inside the step
-        # y clamps of update_d (multi_lane_sim.py:219-222): y < 0 -> 0, y > 6 -> min(y, 7); only steering left over without a
-        # mode flag gets the car there
-        for y0, st in ((0.05, 30.0), (0.3, 30.0), (0.0, 12.0), (6.95, -30.0), (6.6, -30.0), (7.0, -12.0), (6.0, -3.0)):
-            c.append((_sa_case(py=y0, lane=1 if y0 < 3 else 3, vx=20.0, steer=st), ACC))
         # accelerate / maintain corner values: acc < 0 -> 0, acc exactly 5, ceil() ties, cruise from the obstacle ahead
         c.append((_sa_case(vx=7.0, acc=-2.0, flags=F_ACC), ACC))
         c.append((_sa_case(vx=7.0, acc=5.0 - 1.0 / 36.0, flags=F_ACC), ACC))
@@ -98,12 +100,12 @@ def sa_cases(continuous):
     return c
 
 
-def gen_sa_edge(continuous, seed):
+def gen_sa_edge(continuous, seed, offmanifold=False):
     ref = rh.RefSingleAgent(continuous=continuous)
     keys = ("in_car", "in_lane", "in_flags", "in_tick", "in_obst", "in_ncoll", "in_spawn_ctr", "env_id", "action", "out_car", "out_lft",
             "out_obst", "out_obs", "out_rew", "out_done", "out_ncoll", "out_spawn_ctr")
     rec = {k: [] for k in keys}
-    for env_id, (case, a) in enumerate(sa_cases(continuous)):
+    for env_id, (case, a) in enumerate(sa_cases(continuous, offmanifold)):
         st = orc.SaState(1)
         st.car[0] = case["car"]; st.lane[0] = case["lane"]; st.flags[0] = case["flags"]; st.tick[0] = case["tick"]
         st.obst[0] = case["obst"]; st.ncoll[0] = case["ncoll"]; st.spawn_ctr[0] = env_id % 3
@@ -253,7 +255,11 @@ def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     jobs = [("sa_discrete_edge", lambda: gen_sa_edge(False, 41)), ("sa_continuous_edge", lambda: gen_sa_edge(True, 42)),
             ("ma5_discrete_edge", lambda: gen_ma_edge(5, False, 43)), ("ma3_continuous_edge", lambda: gen_ma_edge(3, True, 44)),
-            ("ma2_discrete_edge", lambda: gen_ma_edge(2, False, 45))]
+            ("ma2_discrete_edge", lambda: gen_ma_edge(2, False, 45)),
+            # discrete steering is non-zero only while a lane change is in flight (it is zeroed when the mode ends), so the y clamps of
+            # update_d are unreachable from reset(); these rows start from states the reference itself cannot reach and pin the
+            # clamps for the oracle only (the CUDA kernel's later ticks are specialised to reachable states)
+            ("sa_discrete_offmanifold", lambda: gen_sa_edge(False, 46, offmanifold=True))]
     for name, fn in jobs:
         data = fn()
         path = os.path.join(GOLDEN_DIR, name + ".npz")

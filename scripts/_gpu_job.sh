@@ -1,4 +1,4 @@
-python -m pytest tests/test_reference_gpu.py tests/test_rollout_gpu.py -x -q > gpurun_out/r2o_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/r2o_tests.log
-tail -30 gpurun_out/r2o_tests.log
-ncu --set full --clock-control none --import-source on -k regex:sa_step_kernel -s 20 -c 1 -f -o gpurun_out/prof_sa_r2n_discrete python scripts/perf_sa.py 4194304 > gpurun_out/r2o_ncu_sa.log 2>&1
-tail -5 gpurun_out/r2o_ncu_sa.log
+python -m pytest tests -m gpu -q > gpurun_out/r2q_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/r2q_tests.log
+tail -8 gpurun_out/r2q_tests.log
+HW_N=16384 HW_T=40 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 scripts/nccl_collector_check.py > gpurun_out/r2q_nccl_collector.json 2> gpurun_out/r2q_nccl_collector.err; echo "nccl exit $?"
+cat gpurun_out/r2q_nccl_collector.json; tail -5 gpurun_out/r2q_nccl_collector.err

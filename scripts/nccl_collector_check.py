@@ -68,15 +68,11 @@ def main():
     dist.all_gather(all_d, digest)
     ok &= all(torch.equal(all_d[0], d) for d in all_d)
     if rank == 0:
-        # the NCCL barriers below are not used while rank 0 recomputes; the other ranks just wait at the final barrier
+        # rank 0 recomputes in one process; the other ranks wait at the final barrier
         dist_world = world
-        os.environ["HW_SINGLE"] = "1"
         env = HighwayMAVecEnv(n * world, num_agents=A, continuous=True, seed=5, env_id0=0)
         mem1 = RingMemory(limit, A, env.obs_dim, 2, device=env.device)
         rms1 = RunningMeanStd(shape=(A, env.obs_dim), device=env.device)
-
-        class _Local(RunningMeanStd):
-            pass
         col1 = MADeviceCollector(env, policy_for(0, A), mem1, obs_rms=None, central=False)
         for _ in range(T):
             obs0 = col1.obs[col1.cur]
