@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhighway_b200.so")
-SOURCES = ["hw_sa.cu", "hw_ma.cu", "hw_ma_grp.cu", "hw_policy.cu", "hw_replay.cu"]
+SOURCES = ["hw_sa.cu", "hw_ma.cu", "hw_ma_grp.cu", "hw_ma_tpe.cu", "hw_policy.cu", "hw_replay.cu"]
 HEADERS = ["hw_common.cuh", "hw_ma_common.cuh", os.path.join("..", "..", "include", "highway_b200.h")]
 
 NVCC_FLAGS = [

@@ -84,4 +84,8 @@ __device__ __forceinline__ float norm_f64(double raw, const double lo, const dou
 int ma_grp_launch_step(const HwMaState *st, const void *actions, const HwMaOut *out, const MaConsts &C,
                        uint64_t seed, uint64_t env_id0, int64_t n, int flags, cudaStream_t stream);
 
+// one thread per environment, cars in registers (hw_ma_tpe.cu)
+int ma_tpe_launch_step(const HwMaState *st, const void *actions, const HwMaOut *out, const MaConsts &C,
+                       uint64_t seed, uint64_t env_id0, int64_t n, int flags, cudaStream_t stream);
+
 }  // namespace hw

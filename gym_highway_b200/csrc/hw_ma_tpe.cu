@@ -1,0 +1,544 @@
+// Multi-agent highway step for sm_100a, one THREAD per environment with the cars in registers.
+//
+// Same path as hw_ma_grp.cu (MultiAgentEnv.step, highway_core.HighwaySimulator.act, agent.Car.update_d/update_c,
+// agent.Obstacle.update, check_collisions, Scenario.rewards/observations, DummyVecMAEnv's auto-reset and Monitor's
+// episode record; file:line citations at each stage below).
+//
+// Why a third layout.  With a lane per car (hw_ma_grp.cu) every lane walks through the whole tick - the per-environment
+// stages (leader election, obstacle list, spawn / retire, the tick's control flow) are executed by all five lanes of a
+// group, and the pairwise stages pay shared-memory traffic and warp synchronisation for values that sit in another lane:
+// 7 700 warp-instructions per six env-steps, i.e. 3.5x the thread-instructions per car of the single-agent kernel.  Here
+// a thread owns an environment: the A cars are A-fold unrolled register arrays (A is a template parameter, all indexing
+// is static), so the order-dependent semantics of the reference - cars act and move in id order and see each other's
+// partially updated state - are simply the program order, nothing is published, nothing is synchronised, and the
+// per-environment work is done once.  Only the obstacle list (up to 16 slots x 4 doubles, dynamically indexed) lives in
+// shared memory, in a warp-private [slot][field][lane] layout (conflict free); after the ticks the same region stages the
+// observation rows so that they leave as contiguous 8-byte-per-lane streams (an environment's A rows of 4A+14 floats are
+// contiguous in the output, and so are the 32 environments of a warp).  State loads and stores are coalesced by
+// construction (structure of arrays, consecutive threads = consecutive environments).
+// Cost of the layout: ~165 registers per thread -> 12 warps per SM; the five independent cars of a thread give the
+// instruction-level parallelism that the lower occupancy takes away.
+#include "hw_ma_common.cuh"
+
+namespace hw {
+
+#ifndef HW_TPE_BLOCK
+#define HW_TPE_BLOCK 128
+#endif
+#ifndef HW_TPE_MIN_BLOCKS
+#define HW_TPE_MIN_BLOCKS 3
+#endif
+constexpr int kTpeBlock = HW_TPE_BLOCK;
+constexpr int kTpeWarpDoubles = kMaxK * O_NF * 32;  // one warp's obstacle region: 16 KB
+
+struct TpeOb {  // this thread's column of the warp-private obstacle region
+    double *base;
+    __device__ __forceinline__ double &operator()(int k, int f) const { return base[(k * O_NF + f) * 32]; }
+};
+
+template <int A>
+struct TpeCars {
+    double px[A], py[A], rx[A], vx[A], vy[A], acc[A], steer[A], cruise[A];
+    uint32_t b[A];
+};
+
+__device__ __forceinline__ int tpe_lane(uint32_t b) { return (int)((b >> HW_BITS_LANE_SHIFT) & 3u); }
+__device__ __forceinline__ uint32_t tpe_with_lane(uint32_t b, int lane) { return (b & ~(3u << HW_BITS_LANE_SHIFT)) | ((uint32_t)lane << HW_BITS_LANE_SHIFT); }
+__device__ __forceinline__ double tpe_inf() { return __longlong_as_double(0x7FF0000000000000ll); }
+__device__ __forceinline__ int tpe_overlap(int ax75, int ay37, int bx, int by)
+{
+    // rects are 76 x 38: A overlaps B iff |ax - bx| < 76 and |ay - by| < 38, each as one unsigned compare
+    return (int)(((uint32_t)(ax75 - bx) <= 150u) & ((uint32_t)(ay37 - by) <= 74u));
+}
+
+// start grid: simple_base.py:32-43 ("X" formation, three obstacles behind the cars); counters of the episode cleared
+template <int A>
+__device__ __forceinline__ void tpe_reset(MaHead &h, TpeCars<A> &c, const TpeOb ob)
+{
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const double cx = (a < 2) ? 10.0 : (a == 2) ? 7.5 : 5.0;
+        const int cl = (a == 0 || a == 3) ? 1 : (a == 2) ? 2 : 3;
+        c.px[a] = cx; c.py[a] = lane_centre(cl - 1); c.rx[a] = cx; c.vx[a] = 0.0; c.vy[a] = 0.0; c.acc[a] = 0.0; c.steer[a] = 0.0; c.cruise[a] = 0.0;
+        c.b[a] = (uint32_t)cl << HW_BITS_LANE_SHIFT;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double ox = (k == 0) ? -20.0 : (k == 1) ? -25.0 : -40.0, ov = (k == 0) ? 7.0 : (k == 1) ? 5.0 : 6.0;
+        ob(k, O_PX) = ox; ob(k, O_RX) = ox; ob(k, O_VX) = ov; ob(k, O_IV) = ov;
+    }
+    h.nobs = 3; h.olane = 1u | (2u << 2) | (3u << 4); h.ofresh = 7u;
+    h.newest[0] = 0; h.newest[1] = 1; h.newest[2] = 2;
+    h.tick = 0; h.leader = 0; h.nc_obs = 0; h.nc_agent = 0; h.ep_len = 0; h.ep_ret = 0.0; h.flags = 0;
+}
+
+// spawn (the lane's newest obstacle has fallen behind x = -2.375: highway_core.py:300-323, the old obstacle stays and is slowed
+// down) and retire (what the last car has cleared: :327-342, order preserving compaction).  Rare; kept out of line.
+__device__ __forceinline__ void tpe_spawn_retire(MaHead &h, const TpeOb ob, const int K, const double plead, const double lead_rx,
+                                                     const double last_rx, const uint64_t seed, const uint64_t env_id)
+{
+    for (int lane = 0; lane < 3; ++lane) {
+        const uint32_t s = h.newest[lane];
+        if (s >= 31u) continue;  // the lane's newest obstacle was retired: the reference never spawns there again
+        if (ob((int)s, O_PX) < -2.375) {
+            double u1, u2;
+            spawn_uniforms(seed, env_id, h.spawn_ctr, u1, u2);
+            h.spawn_ctr += 1;
+            const double x = dadd(70.0, dmul(30.0, u1)), v = dadd(5.0, dmul(2.0, u2));
+            const double ovx = ob((int)s, O_VX);
+            const double m = (ovx < v) ? ovx : v;  // min(rand_vel_x, obstacle.velocity.x)
+            ob((int)s, O_VX) = m; ob((int)s, O_IV) = m;
+            if ((int)h.nobs < K) {
+                const int nk = (int)h.nobs;
+                ob(nk, O_PX) = x; ob(nk, O_RX) = dadd(lead_rx, dsub(x, plead));
+                ob(nk, O_VX) = v; ob(nk, O_IV) = v;
+                h.olane = (h.olane & ~(3u << (2 * nk))) | ((uint32_t)(lane + 1) << (2 * nk));
+                h.ofresh |= 1u << nk;
+                h.newest[lane] = (uint32_t)nk;
+                h.nobs += 1;
+            } else {
+                h.flags |= 1u;  // out of slots: the spawn is dropped (tests require this never to happen)
+            }
+        }
+    }
+    const double thr = dsub(dsub(-2.375, plead), 2.0);
+    int w = 0;
+    uint32_t nl = 0, nf = 0, nn0 = 31u, nn1 = 31u, nn2 = 31u;
+    for (int k = 0; k < (int)h.nobs; ++k) {
+        if (dsub(ob(k, O_RX), last_rx) < thr) continue;
+        if (w != k) { ob(w, O_PX) = ob(k, O_PX); ob(w, O_RX) = ob(k, O_RX); ob(w, O_VX) = ob(k, O_VX); ob(w, O_IV) = ob(k, O_IV); }
+        nl |= (uint32_t)ob_lane(h, k) << (2 * w);
+        nf |= ((h.ofresh >> k) & 1u) << w;
+        if (h.newest[0] == (uint32_t)k) nn0 = (uint32_t)w;
+        if (h.newest[1] == (uint32_t)k) nn1 = (uint32_t)w;
+        if (h.newest[2] == (uint32_t)k) nn2 = (uint32_t)w;
+        ++w;
+    }
+    h.nobs = (uint32_t)w; h.olane = nl; h.ofresh = nf; h.newest[0] = nn0; h.newest[1] = nn1; h.newest[2] = nn2;
+}
+
+// one world.act() followed by Scenario.rewards() (highway_core.py:245-399, simple_base.py:65-80); returns the cars that collided
+template <int A, bool CONT, bool EXACT>
+__device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const TpeOb ob, const int K, const MaConsts &C, const double dt,
+                                             const bool inf_obs, const uint32_t (&amask)[A], const double (&a0)[A], const double (&a1)[A],
+                                             const uint64_t seed, const uint64_t env_id, uint32_t &done)
+{
+    h.tick += 1;
+    if (h.tick >= (uint32_t)C.timeout_tick) done |= (1u << A) - 1u;  // highway_core.py:276-277
+
+    // ---- actions for every car in id order (highway_core.py:280-281, :110-188): maintain() of car a sees the lanes the cars
+    //      before it have just switched to and the old lanes of the cars after it - program order ----
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        if (CONT) {
+            c.acc[a] = py_clamp(dadd(c.acc[a], a0[a]), -5.0, 5.0);
+            c.steer[a] = py_clamp(dadd(c.steer[a], a1[a]), -30.0, 30.0);
+            continue;
+        }
+        // amask = the mode bit the action asks for; it fires when not yet set.  The two modes of a pair exclude each other, so
+        // setting the bit and clearing its partner is the identity when nothing fires.
+        const uint32_t am = amask[a];
+        const uint32_t apair = am | ((am & (kBitLeft | kBitDoAcc)) << 1) | ((am & (kBitRight | kBitDoMaint)) >> 1);
+        const uint32_t fire = am & ~c.b[a];
+        uint32_t b = (c.b[a] & ~apair) | am;
+        int lane = tpe_lane(b);
+        if (fire & kBitDoMaint) {
+            // all_obstacles iterates the cars (id order) and then the obstacles (insertion order): nearest strictly ahead in the lane,
+            // first wins ties
+            double bpx = tpe_inf(), bvx = c.vx[a];
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                if (j == a) continue;
+                const bool take = (tpe_lane(c.b[j]) == lane) & (c.px[j] > c.px[a]) & (c.px[j] < bpx);
+                dmov_if(take, bpx, c.px[j]); dmov_if(take, bvx, c.vx[j]);
+            }
+            const uint32_t diff = h.olane ^ ((uint32_t)lane * 0x55555555u);
+            uint32_t same = ~(diff | (diff >> 1)) & 0x55555555u & live_mask(h.nobs);
+            while (same) {
+                const int k = (__ffs((int)same) - 1) >> 1;
+                same &= same - 1u;
+                const double opx = ob(k, O_PX), ovx = ob(k, O_VX);
+                const bool take = (opx > c.px[a]) & (opx < bpx);
+                dmov_if(take, bpx, opx); dmov_if(take, bvx, ovx);
+            }
+            c.cruise[a] = bvx;
+        }
+        const int dl = (int)((fire >> 19) & 1u) - (int)((fire >> 18) & 1u);  // RIGHT +1, LEFT -1, only when it fires
+        lane = min(max(lane + dl, 1), 3);
+        c.acc[a] = py_clamp(c.acc[a], -5.0, 5.0);
+        c.steer[a] = py_clamp(c.steer[a], -30.0, 30.0);
+        c.b[a] = tpe_with_lane(b, lane);
+    }
+
+    // ---- car updates in id order against last tick's leader (agent.py:79-165): a car subtracts the leader's velocity "as it is
+    //      now" (agent.py:147-151) - its new value for the cars after it in id order, its old one for those before ----
+    const int L = (int)h.leader;
+    double lv = c.vx[0];
+#pragma unroll
+    for (int j = 1; j < A; ++j) dmov_if(L == j, lv, c.vx[j]);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        uint32_t b = c.b[a];
+        if (!CONT) {
+            const bool m_acc = (b & kBitDoAcc) != 0, m_maint = (b & kBitDoMaint) != 0;  // never both
+            double acc_a = dadd(c.acc[a], dt);
+            dset_if(c.acc[a] < 0.0, acc_a, 0.0);
+            const double vc = ceil(c.vx[a]), cc = ceil(c.cruise[a]);
+            const bool snap = m_maint && vc == cc;
+            const double acc_m = __hiloint2double(snap ? 0 : ((vc <= cc) ? 0x40140000 : (int)0xC0140000), 0);  // 0.0, 5.0, -5.0
+            dmov_if_nz(b & kBitDoAcc, c.acc[a], acc_a);
+            dmov_if_nz(b & kBitDoMaint, c.acc[a], acc_m);
+            dmov_if(snap, c.vx[a], c.cruise[a]);
+            if (m_acc && c.acc[a] == 5.0) b &= ~kBitDoAcc;
+            if (snap) b &= ~kBitDoMaint;
+        }
+        c.vx[a] = py_clamp(dadd(c.vx[a], dmul(c.acc[a], dt)), 0.0, 20.0);
+        if (!CONT) {
+            const int lane = tpe_lane(b);
+            const double ty = __hiloint2double(lane == 1 ? 0x3FF40000 : (lane == 2 ? 0x400E0000 : 0x40190000), 0);  // 1.25, 3.75, 6.25
+            const bool m_left = (b & kBitLeft) != 0, m_right = (b & kBitRight) != 0;  // never both
+            double inc = 0.0;
+            dmov_if(m_left, inc, C.k30dt); dmov_if(m_right, inc, -C.k30dt);
+            c.steer[a] = dadd(c.steer[a], inc);  // + 0.0 is the identity on every value steer can hold
+            const bool reached = (m_left && c.py[a] <= ty) || (m_right && c.py[a] >= ty);
+            dset_if(reached, c.steer[a], 0.0);
+            if (reached) b &= ~(kBitLeft | kBitRight);
+        }
+        double ang = 0.0;
+        if (c.steer[a] != 0.0) ang = angular_velocity<EXACT>(c.vx[a], c.steer[a]);
+        if (!CONT) c.vy[a] = ang;  // agent.py:144: velocity.y = angular_velocity (discrete update only)
+        dmov_if(L == a, lv, c.vx[a]);
+        const double vdt = dmul(c.vx[a], dt);
+        double px = dadd(c.px[a], vdt);
+        double py = dadd(c.py[a], dmul(c.vy[a], dt));
+        if (CONT) py = dsub(py, dmul(ang, dt));
+        else      py = dsub(py, dmul(dmul(dmul(ang, kRad2Deg), dt), dt));
+        px = dsub(px, dmul(lv, dt));
+        dset_if(L == a, px, 10.0);
+        dset_if(7.0 < py, py, 7.0);   // if y < 1: y = 1 elif y > 6: y = min(y, 7)
+        dset_if(py < 1.0, py, 1.0);
+        c.rx[a] = dadd(c.rx[a], vdt);
+        c.px[a] = px; c.py[a] = py;
+        if (CONT) {
+            const double d0 = fabs(dsub(py, 1.25)), d1 = fabs(dsub(py, 3.75)), d2 = fabs(dsub(py, 6.25));
+            b = tpe_with_lane(b, (d0 <= d1 && d0 <= d2) ? 1 : (d1 <= d2) ? 2 : 3);
+        }
+        c.b[a] = b;
+    }
+    const double lvdt = dmul(lv, dt);  // last tick's leader, this tick's velocity
+
+    // ---- leader / last election: stable sort of the cars by x, descending (highway_core.py:294-297).  In the reference it follows
+    //      the obstacle updates, but it only reads the cars, which are final by now ----
+    int lead = 0, last = 0;
+    double plead = c.px[0], plast = c.px[0], lead_rx = c.rx[0], last_rx = c.rx[0];
+#pragma unroll
+    for (int j = 1; j < A; ++j) {
+        const bool up = c.px[j] > plead, dn = c.px[j] <= plast;  // first of the maxima, last of the minima
+        lead = up ? j : lead; dmov_if(up, plead, c.px[j]); dmov_if(up, lead_rx, c.rx[j]);
+        last = dn ? j : last; dmov_if(dn, plast, c.px[j]); dmov_if(dn, last_rx, c.rx[j]);
+    }
+    h.leader = (uint32_t)lead;
+    (void)last;
+
+    // ---- obstacle updates (agent.py:223-260): yield to the nearest car ahead in the lane, by raw x; the slot is tested for a
+    //      spawn / retire while its values are in registers ----
+    const double thr = dsub(dsub(-2.375, plead), 2.0);
+    const uint32_t newest_mask = (1u << h.newest[0]) | (1u << h.newest[1]) | (1u << h.newest[2]);  // 31 = retired: matches no slot
+    bool want = false;
+    for (int k = 0; k < (int)h.nobs; ++k) {
+        const int lane = ob_lane(h, k);
+        const double orx = ob(k, O_RX), iv = ob(k, O_IV);
+        double bd = tpe_inf(), bv = iv;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            const double d = dsub(c.rx[j], orx);
+            const bool take = (tpe_lane(c.b[j]) == lane) & (orx < c.rx[j]) & (d < bd);  // first wins ties
+            dmov_if(take, bd, d); dmov_if(take, bv, c.vx[j]);
+        }
+        double v = py_clamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
+        dmov_if(bd < tpe_inf(), v, iv);        // else min(init_vx, that car's vx)
+        dmov_if(bv < iv, v, bv);
+        const double odt = dmul(v, dt);
+        const double opx = dsub(dadd(ob(k, O_PX), odt), lvdt);
+        const double orx2 = dadd(orx, odt);
+        ob(k, O_VX) = v; ob(k, O_PX) = opx; ob(k, O_RX) = orx2;
+        want = want | ((((newest_mask >> k) & 1u) != 0u) & (opx < -2.375)) | (dsub(orx2, last_rx) < thr);
+    }
+    h.ofresh = 0;  // every live obstacle has now written its rect
+    if (inf_obs && want) tpe_spawn_retire(h, ob, K, plead, lead_rx, last_rx, seed, env_id);
+
+    // ---- Scenario.rewards -> check_collisions, after the updates and spawns of this tick (highway_core.py:401-422) ----
+    int ax75[A], ay37[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) { ax75[a] = rect_x(c.px[a]) + 75; ay37[a] = rect_y(c.py[a]) + 37; }
+    uint32_t hit = 0;
+    int no = 0, na = 0;
+    for (int k = 0; k < (int)h.nobs; ++k) {
+        const bool fresh = ((h.ofresh >> k) & 1u) != 0u;  // spawned in this tick: still pygame's default rect (0, 0, 76, 38)
+        const int bx = fresh ? 0 : rect_x(ob(k, O_PX));
+        const int by = fresh ? 0 : 80 * ob_lane(h, k) - 59;  // y = 21 + 80 * (lane - 1)
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const int o = tpe_overlap(ax75[a], ay37[a], bx, by);
+            no += o; hit |= (uint32_t)o << a;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+#pragma unroll
+        for (int j = a + 1; j < A; ++j) {
+            const int o = tpe_overlap(ax75[a], ay37[a], ax75[j] - 75, ay37[j] - 37);
+            na += 2 * o; hit |= ((uint32_t)o << a) | ((uint32_t)o << j);
+        }
+    }
+    h.nc_obs += (uint32_t)no; h.nc_agent += (uint32_t)na;
+    done |= hit;
+    return hit;
+}
+
+// MultiAgentEnv._get_obs_norm (highway_env.py:139-149) of one value: see norm_f64
+// Scenario.observations (simple_base.py:82-154): the part that needs the obstacle list - per car and lane the obstacle nearest in
+// raw x (first wins ties, insertion order) as two normalised floats {dx, dvx}; a lane without an obstacle (the reference raises
+// there) is flagged and reads 0.5
+template <int A>
+__device__ __forceinline__ uint32_t tpe_observe_obstacles(MaHead &h, const TpeCars<A> &c, const TpeOb ob, float (&odx)[A][3], float (&odv)[A][3])
+{
+    const uint32_t live = live_mask(h.nobs);
+    uint32_t nolane = 0;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const uint32_t diff = h.olane ^ ((uint32_t)(l + 1) * 0x55555555u);
+        uint32_t same = ~(diff | (diff >> 1)) & 0x55555555u & live;
+        double nd[A], brx[A], bvx[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) { nd[a] = tpe_inf(); brx[a] = 0.0; bvx[a] = 0.0; }
+        const bool none = same == 0u;
+        while (same) {
+            const int k = (__ffs((int)same) - 1) >> 1;
+            same &= same - 1u;
+            const double krx = ob(k, O_RX), kvx = ob(k, O_VX);
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const double d = fabs(dsub(c.rx[a], krx));
+                const bool take = d < nd[a];
+                dmov_if(take, nd[a], d); dmov_if(take, brx[a], krx); dmov_if(take, bvx[a], kvx);
+            }
+        }
+        if (none) { h.flags |= 2u; nolane |= 1u << l; }
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            odx[a][l] = none ? 0.5f : norm_f64(dsub(brx[a], c.rx[a]), -60.0, 60.0);
+            odv[a][l] = none ? 0.5f : norm_f64(dsub(bvx[a], c.vx[a]), -20.0, 20.0);
+        }
+    }
+    return nolane;
+}
+
+// the 4A+14 floats of car a as 2A+7 float2 (simple_base.py:94-154 + highway_env.py:139-149), written through `put(q, value)`
+template <int A, typename Put>
+__device__ __forceinline__ void tpe_observe_row(const TpeCars<A> &c, const int a, const float (&odx)[A][3], const float (&odv)[A][3],
+                                                const uint32_t nolane, Put put)
+{
+    constexpr int S = A + 2;
+    put(0, make_float2(norm_f64(c.acc[a], -5.0, 5.0), norm_f64(c.steer[a], -30.0, 30.0)));
+    put(1, make_float2(norm_f64(c.rx[a], 0.0, 1200.0), norm_f64(c.py[a], 0.0, 8.0)));
+    put(2 + S, make_float2(norm_f64(c.vx[a], -20.0, 20.0), norm_f64(c.vy[a], -20.0, 20.0)));
+#pragma unroll
+    for (int j = 0; j < A; ++j) {  // other cars: car j goes to slot j - (j > a)
+        if (j == a) continue;
+        const int sl = j - (j > a ? 1 : 0);
+        put(2 + sl, make_float2(norm_f64(dsub(c.rx[j], c.rx[a]), -60.0, 60.0), norm_f64(dsub(c.py[j], c.py[a]), -8.0, 8.0)));
+        put(3 + S + sl, make_float2(norm_f64(dsub(c.vx[j], c.vx[a]), -20.0, 20.0), norm_f64(dsub(c.vy[j], c.vy[a]), -20.0, 20.0)));
+    }
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {  // obstacles: slot A - 1 + lane
+        const int s = A - 1 + l;
+        const bool none = ((nolane >> l) & 1u) != 0u;
+        const float dy = none ? 0.5f : norm_f64(dsub(lane_centre(l), c.py[a]), -8.0, 8.0);
+        const float dvy = none ? 0.5f : norm_f64(dsub(0.0, c.vy[a]), -20.0, 20.0);
+        put(2 + s, make_float2(odx[a][l], dy));
+        put(3 + S + s, make_float2(odv[a][l], dvy));
+    }
+}
+
+template <int A, bool CONT, bool EXACT>
+__global__ void __launch_bounds__(kTpeBlock, HW_TPE_MIN_BLOCKS)
+ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew,
+                   uint8_t *__restrict__ done_out, double *__restrict__ term, unsigned long long *__restrict__ stats,
+                   const MaConsts C, const uint64_t seed, const uint64_t env_id0, const int64_t n, const int flags)
+{
+    extern __shared__ double sm_dyn[];
+    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *wbase = sm_dyn + (size_t)warp * kTpeWarpDoubles;
+    const TpeOb ob{wbase + lane_id};
+    const int64_t i0 = (int64_t)blockIdx.x * kTpeBlock + warp * 32;  // first environment of this warp
+    const int64_t i = i0 + lane_id;
+    const bool live = i < n;
+    const bool inf_obs = !(flags & HW_FLAG_NO_INF_OBS);
+    const bool autoreset = !(flags & HW_FLAG_NO_AUTORESET);
+    const bool shared_reward = (flags & HW_FLAG_SHARED_REWARD) != 0;
+    const int K = S.K;
+    const double dt = C.dt;
+    constexpr int D2 = 2 * A + 7;  // float2 per observation row
+    long long acc[7] = {0, 0, 0, 0, 0, 0, 0};  // this thread's finished episode, summed per warp at the end
+
+    MaHead h;
+    TpeCars<A> c;
+    uint32_t done = 0, hit = 0;
+    float odx[A][3], odv[A][3];
+    uint32_t nolane = 0;
+    if (live) {
+        ma_load_head(h, S, i, n);
+        // is_done persists until reset() (highway_core.py:239, :420): with HW_FLAG_NO_AUTORESET a car that finished in an earlier
+        // step is still done, and the step then ends after its first tick (highway_env.py:85-86)
+        done = (h.flags >> 8) & 31u; h.flags &= 0xFFu;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const float *p = S.cars + (int64_t)(a * 9) * n + i;
+            c.px[a] = (double)p[0]; c.py[a] = (double)p[n]; c.rx[a] = (double)p[2 * n]; c.vx[a] = (double)p[3 * n]; c.vy[a] = (double)p[4 * n];
+            c.acc[a] = (double)p[5 * n]; c.steer[a] = (double)p[6 * n]; c.cruise[a] = (double)p[7 * n];
+            c.b[a] = __float_as_uint(p[8 * n]);
+        }
+        for (int k = 0; k < (int)h.nobs; ++k) {
+            const float4 o = S.obst[(int64_t)k * n + i];
+            ob(k, O_PX) = o.x; ob(k, O_RX) = o.y; ob(k, O_VX) = o.z; ob(k, O_IV) = o.w;
+        }
+        uint32_t amask[A];
+        double a0[A], a1[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            amask[a] = 0; a0[a] = 0.0; a1[a] = 0.0;
+            if (CONT) {
+                const float2 v = reinterpret_cast<const float2 *>(actions)[i * A + a];
+                a0[a] = dmul(dmul((double)v.x, 5.0), dt);
+                a1[a] = dmul(dmul((double)v.y, 30.0), dt);
+            } else {
+                const int act = reinterpret_cast<const int *>(actions)[i * A + a];
+                amask[a] = ((uint32_t)act < 4u) ? (kBitLeft << act) : 0u;  // LEFT, RIGHT, ACCELERATE, MAINTAIN = bits 18..21
+            }
+        }
+        const uint64_t env_id = env_id0 + (uint64_t)i;
+        for (int t = 0; t < C.ticks_per_step; ++t) {
+            hit = tpe_tick<A, CONT, EXACT>(h, c, ob, K, C, dt, inf_obs, amask, a0, a1, seed, env_id, done);
+            if (done) break;  // highway_env.py:85-86: the step ends with the first tick that finishes a car
+        }
+
+        // rewards of the step (Scenario.rewards of the last tick that ran, simple_base.py:65-80): -250 for a car that collided in it,
+        // else v.x / 20 - 1; summed in id order for shared_reward (highway_env.py:92-94) and for Monitor
+        double r[A], rsum = 0.0;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            r[a] = dsub(ddiv_const(c.vx[a], 20.0), 1.0);
+            dset_if(((hit >> a) & 1u) != 0u, r[a], -250.0);
+            rsum = dadd(rsum, r[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const double ra = shared_reward ? rsum : r[a];
+            h.ep_ret = dadd(h.ep_ret, ra);  // Monitor sums the python floats of every agent and step
+            rew[i * A + a] = (float)ra;
+            done_out[i * A + a] = (done >> a) & 1u;
+        }
+        h.ep_len += 1;
+        if (done) {
+            if (term) {
+                double *tm = term + 5 * i;
+                tm[0] = (double)h.tick; tm[1] = (double)h.nc_obs; tm[2] = (double)h.nc_agent; tm[3] = h.ep_ret; tm[4] = (double)h.ep_len;
+            }
+            acc[0] = 1; acc[1] = h.ep_len; acc[2] = __double2ll_rn(h.ep_ret * 1000.0); acc[3] = h.nc_obs;
+            acc[4] = (h.tick >= (uint32_t)C.timeout_tick) ? 1 : 0; acc[5] = h.nc_agent; acc[6] = h.flags & 1u;
+            if (autoreset) {
+                const uint32_t keep = h.flags;
+                tpe_reset<A>(h, c, ob);
+                h.flags = keep;  // sticky diagnostics survive the reset
+            }
+        }
+        if (!(done && autoreset)) h.flags |= done << 8;
+
+        // the part of the observation that reads the obstacle list, then the state goes back to HBM (fp32) and the list's
+        // shared memory is free for the staging of the rows
+        nolane = tpe_observe_obstacles<A>(h, c, ob, odx, odv);
+        ma_store_head(h, S, i, n);
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            float *p = S.cars + (int64_t)(a * 9) * n + i;
+            p[0] = (float)c.px[a]; p[n] = (float)c.py[a]; p[2 * n] = (float)c.rx[a]; p[3 * n] = (float)c.vx[a]; p[4 * n] = (float)c.vy[a];
+            p[5 * n] = (float)c.acc[a]; p[6 * n] = (float)c.steer[a]; p[7 * n] = (float)c.cruise[a];
+            p[8 * n] = __uint_as_float(c.b[a]);
+        }
+        for (int k = 0; k < (int)h.nobs; ++k)
+            S.obst[(int64_t)k * n + i] = make_float4((float)ob(k, O_PX), (float)ob(k, O_RX), (float)ob(k, O_VX), (float)ob(k, O_IV));
+    }
+
+    // observation rows: staged in the warp's (now free) shared region, kPass cars at a time, and streamed out 8 bytes per lane -
+    // consecutive lanes write consecutive addresses of the environments' contiguous [A][4A+14] blocks
+    constexpr int kPass = (kTpeWarpDoubles / 32) / D2 < A ? (kTpeWarpDoubles / 32) / D2 : A;  // cars per pass that fit the region
+    float2 *stage = reinterpret_cast<float2 *>(wbase);
+    float2 *out2 = reinterpret_cast<float2 *>(obs);
+#pragma unroll
+    for (int c0 = 0; c0 < A; c0 += kPass) {
+        const int cn = (A - c0 < kPass) ? A - c0 : kPass;  // cars in this pass
+        __syncwarp();  // every lane is done with the region (obstacle reads / the previous pass's copy)
+        if (live) {
+#pragma unroll
+            for (int a = c0; a < c0 + kPass; ++a) {
+                if (a >= A) break;
+                float2 *row = stage + (size_t)lane_id * (cn * D2) + (a - c0) * D2;
+                tpe_observe_row<A>(c, a, odx, odv, nolane, [&](int q, float2 v) { row[q] = v; });
+            }
+        }
+        __syncwarp();
+        const int per_env = cn * D2;
+        for (int idx = lane_id; idx < 32 * per_env; idx += 32) {
+            const int e = idx / per_env, q = idx - e * per_env;
+            if (i0 + e < n) out2[(i0 + e) * (int64_t)(A * D2) + c0 * D2 + q] = stage[idx];
+        }
+    }
+
+    if (stats) {
+        if (__any_sync(0xffffffffu, acc[0] != 0)) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) acc[j] = warp_sum(acc[j]);
+            if (lane_id == 0) {
+#pragma unroll
+                for (int j = 0; j < 7; ++j) atomicAdd(&stats[j], (unsigned long long)acc[j]);
+            }
+        }
+    }
+}
+
+template <int A>
+static int ma_tpe_launch_a(const MaPtrs &S, const void *actions, const HwMaOut *out, const MaConsts &C_, uint64_t seed, uint64_t env_id0,
+                           int64_t n, int flags, cudaStream_t stream)
+{
+    const size_t smem = (size_t)(kTpeBlock / 32) * kTpeWarpDoubles * sizeof(double);
+    const unsigned grid = (unsigned)((n + kTpeBlock - 1) / kTpeBlock);
+    cudaError_t e = cudaSuccess;
+#define HW_TPE_LAUNCH(CT, EX) do { \
+        e = cudaFuncSetAttribute(ma_tpe_step_kernel<A, CT, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return (int)e; \
+        ma_tpe_step_kernel<A, CT, EX><<<grid, kTpeBlock, smem, stream>>>(S, actions, out->obs, out->rew, out->done, out->term, out->stats, C_, seed, env_id0, n, flags); \
+    } while (0)
+    const bool exact = (flags & HW_FLAG_EXACT_STEERING) != 0;
+    if (flags & HW_FLAG_CONTINUOUS) { if (exact) HW_TPE_LAUNCH(true, true); else HW_TPE_LAUNCH(true, false); }
+    else                            { if (exact) HW_TPE_LAUNCH(false, true); else HW_TPE_LAUNCH(false, false); }
+#undef HW_TPE_LAUNCH
+    return (int)cudaGetLastError();
+}
+
+int ma_tpe_launch_step(const HwMaState *st, const void *actions, const HwMaOut *out, const MaConsts &C_,
+                       uint64_t seed, uint64_t env_id0, int64_t n, int flags, cudaStream_t stream)
+{
+    MaPtrs S;
+    S.cars = st->cars; S.obst = reinterpret_cast<float4 *>(st->obst); S.head = st->head; S.A = st->num_agents; S.K = st->num_slots;
+    switch (S.A) {
+    case 1: return ma_tpe_launch_a<1>(S, actions, out, C_, seed, env_id0, n, flags, stream);
+    case 2: return ma_tpe_launch_a<2>(S, actions, out, C_, seed, env_id0, n, flags, stream);
+    case 3: return ma_tpe_launch_a<3>(S, actions, out, C_, seed, env_id0, n, flags, stream);
+    case 4: return ma_tpe_launch_a<4>(S, actions, out, C_, seed, env_id0, n, flags, stream);
+    case 5: return ma_tpe_launch_a<5>(S, actions, out, C_, seed, env_id0, n, flags, stream);
+    }
+    return HW_E_BADARG;
+}
+
+}  // namespace hw

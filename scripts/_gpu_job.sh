@@ -1,4 +1,4 @@
-python -m pytest tests -m gpu -q > gpurun_out/r2q_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/r2q_tests.log
-tail -8 gpurun_out/r2q_tests.log
-HW_N=16384 HW_T=40 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 scripts/nccl_collector_check.py > gpurun_out/r2q_nccl_collector.json 2> gpurun_out/r2q_nccl_collector.err; echo "nccl exit $?"
-cat gpurun_out/r2q_nccl_collector.json; tail -5 gpurun_out/r2q_nccl_collector.err
+python -m pytest tests/test_ma_gpu.py tests/test_reference_gpu.py -x -q -k "thread or golden or vecenv" > gpurun_out/r2t_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/r2t_tests.log
+tail -25 gpurun_out/r2t_tests.log
+HW_MA_KERNEL=thread python scripts/perf_ma.py 16384 262144 2>&1 | tail -4
+python scripts/perf_ma.py 16384 262144 2>&1 | tail -4

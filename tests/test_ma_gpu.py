@@ -67,9 +67,10 @@ def test_golden_transitions(name, kernel):
 
 
 @pytest.mark.parametrize("A,continuous,kernel", [(5, False, "group"), (5, True, "group"), (3, False, "group"), (1, True, "group"),
-                                                 (4, False, "group"), (2, True, "group"), (5, False, "thread")])
+                                                 (4, False, "group"), (2, True, "group"), (5, False, "thread"), (5, True, "thread"),
+                                                 (3, False, "thread"), (1, True, "thread"), (4, False, "thread"), (2, True, "thread")])
 def test_trajectory_parity(A, continuous, kernel):
-    n, steps, seed = 2048 if kernel == "group" else 1000, 400, 9
+    n, steps, seed = 2048 if kernel == "group" else 1000 + 37, 400, 9   # 1037: a ragged last warp for the thread-per-env kernel
     env = _env(n, A, continuous=continuous, seed=seed, env_id0=7, exact_steering=True, kernel=kernel)
     st = mo.MaState(n, A)
     mo.ma_reset(st)
@@ -101,7 +102,7 @@ def test_trajectory_parity(A, continuous, kernel):
     assert env.episode_statistics()["episodes"] == nd
 
 
-@pytest.mark.parametrize("kernel", ["group"])
+@pytest.mark.parametrize("kernel", ["group", "thread"])
 def test_done_flags_persist_without_autoreset(kernel):
     """gym per-env semantics (HW_FLAG_NO_AUTORESET): `is_done` lives until reset() in the reference (highway_core.py:239, :420),
     so a car that finished in an earlier step still reports done, and every later step ends after its first tick
