@@ -39,7 +39,8 @@ struct TpeOb {  // this thread's column of the warp-private obstacle region
 template <int A>
 struct TpeCars {
     double px[A], py[A], rx[A], vx[A], vy[A], acc[A], steer[A], cruise[A];
-    uint32_t b[A];
+    uint32_t b[A];  // mode bits; the lane field of the packed word is kept apart in ln[] while the state is in registers
+    int ln[A];
 };
 
 __device__ __forceinline__ int tpe_lane(uint32_t b) { return (int)((b >> HW_BITS_LANE_SHIFT) & 3u); }
@@ -60,7 +61,7 @@ __device__ __forceinline__ void tpe_reset(MaHead &h, TpeCars<A> &c, const TpeOb 
         const double cx = (a < 2) ? 10.0 : (a == 2) ? 7.5 : 5.0;
         const int cl = (a == 0 || a == 3) ? 1 : (a == 2) ? 2 : 3;
         c.px[a] = cx; c.py[a] = lane_centre(cl - 1); c.rx[a] = cx; c.vx[a] = 0.0; c.vy[a] = 0.0; c.acc[a] = 0.0; c.steer[a] = 0.0; c.cruise[a] = 0.0;
-        c.b[a] = (uint32_t)cl << HW_BITS_LANE_SHIFT;
+        c.b[a] = 0; c.ln[a] = cl;
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -117,157 +118,11 @@ __device__ __forceinline__ void tpe_spawn_retire(MaHead &h, const TpeOb ob, cons
     h.nobs = (uint32_t)w; h.olane = nl; h.ofresh = nf; h.newest[0] = nn0; h.newest[1] = nn1; h.newest[2] = nn2;
 }
 
-// one world.act() followed by Scenario.rewards() (highway_core.py:245-399, simple_base.py:65-80); returns the cars that collided
-template <int A, bool CONT, bool EXACT>
-__device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const TpeOb ob, const int K, const MaConsts &C, const double dt,
-                                             const bool inf_obs, const uint32_t (&amask)[A], const double (&a0)[A], const double (&a1)[A],
-                                             const uint64_t seed, const uint64_t env_id, uint32_t &done)
+// exact check_collisions over the current obstacle list (fresh slots carry pygame's default rect) and the other cars: counters,
+// and the mask of the cars that collided.  Only reached when the tick's filter saw an overlap.
+template <int A>
+__device__ __forceinline__ uint32_t tpe_collide_exact(MaHead &h, const TpeCars<A> &c, const TpeOb ob)
 {
-    h.tick += 1;
-    if (h.tick >= (uint32_t)C.timeout_tick) done |= (1u << A) - 1u;  // highway_core.py:276-277
-
-    // ---- actions for every car in id order (highway_core.py:280-281, :110-188): maintain() of car a sees the lanes the cars
-    //      before it have just switched to and the old lanes of the cars after it - program order ----
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-        if (CONT) {
-            c.acc[a] = py_clamp(dadd(c.acc[a], a0[a]), -5.0, 5.0);
-            c.steer[a] = py_clamp(dadd(c.steer[a], a1[a]), -30.0, 30.0);
-            continue;
-        }
-        // amask = the mode bit the action asks for; it fires when not yet set.  The two modes of a pair exclude each other, so
-        // setting the bit and clearing its partner is the identity when nothing fires.
-        const uint32_t am = amask[a];
-        const uint32_t apair = am | ((am & (kBitLeft | kBitDoAcc)) << 1) | ((am & (kBitRight | kBitDoMaint)) >> 1);
-        const uint32_t fire = am & ~c.b[a];
-        uint32_t b = (c.b[a] & ~apair) | am;
-        int lane = tpe_lane(b);
-        if (fire & kBitDoMaint) {
-            // all_obstacles iterates the cars (id order) and then the obstacles (insertion order): nearest strictly ahead in the lane,
-            // first wins ties
-            double bpx = tpe_inf(), bvx = c.vx[a];
-#pragma unroll
-            for (int j = 0; j < A; ++j) {
-                if (j == a) continue;
-                const bool take = (tpe_lane(c.b[j]) == lane) & (c.px[j] > c.px[a]) & (c.px[j] < bpx);
-                dmov_if(take, bpx, c.px[j]); dmov_if(take, bvx, c.vx[j]);
-            }
-            const uint32_t diff = h.olane ^ ((uint32_t)lane * 0x55555555u);
-            uint32_t same = ~(diff | (diff >> 1)) & 0x55555555u & live_mask(h.nobs);
-            while (same) {
-                const int k = (__ffs((int)same) - 1) >> 1;
-                same &= same - 1u;
-                const double opx = ob(k, O_PX), ovx = ob(k, O_VX);
-                const bool take = (opx > c.px[a]) & (opx < bpx);
-                dmov_if(take, bpx, opx); dmov_if(take, bvx, ovx);
-            }
-            c.cruise[a] = bvx;
-        }
-        const int dl = (int)((fire >> 19) & 1u) - (int)((fire >> 18) & 1u);  // RIGHT +1, LEFT -1, only when it fires
-        lane = min(max(lane + dl, 1), 3);
-        c.acc[a] = py_clamp(c.acc[a], -5.0, 5.0);
-        c.steer[a] = py_clamp(c.steer[a], -30.0, 30.0);
-        c.b[a] = tpe_with_lane(b, lane);
-    }
-
-    // ---- car updates in id order against last tick's leader (agent.py:79-165): a car subtracts the leader's velocity "as it is
-    //      now" (agent.py:147-151) - its new value for the cars after it in id order, its old one for those before ----
-    const int L = (int)h.leader;
-    double lv = c.vx[0];
-#pragma unroll
-    for (int j = 1; j < A; ++j) dmov_if(L == j, lv, c.vx[j]);
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-        uint32_t b = c.b[a];
-        if (!CONT) {
-            const bool m_acc = (b & kBitDoAcc) != 0, m_maint = (b & kBitDoMaint) != 0;  // never both
-            double acc_a = dadd(c.acc[a], dt);
-            dset_if(c.acc[a] < 0.0, acc_a, 0.0);
-            const double vc = ceil(c.vx[a]), cc = ceil(c.cruise[a]);
-            const bool snap = m_maint && vc == cc;
-            const double acc_m = __hiloint2double(snap ? 0 : ((vc <= cc) ? 0x40140000 : (int)0xC0140000), 0);  // 0.0, 5.0, -5.0
-            dmov_if_nz(b & kBitDoAcc, c.acc[a], acc_a);
-            dmov_if_nz(b & kBitDoMaint, c.acc[a], acc_m);
-            dmov_if(snap, c.vx[a], c.cruise[a]);
-            if (m_acc && c.acc[a] == 5.0) b &= ~kBitDoAcc;
-            if (snap) b &= ~kBitDoMaint;
-        }
-        c.vx[a] = py_clamp(dadd(c.vx[a], dmul(c.acc[a], dt)), 0.0, 20.0);
-        if (!CONT) {
-            const int lane = tpe_lane(b);
-            const double ty = __hiloint2double(lane == 1 ? 0x3FF40000 : (lane == 2 ? 0x400E0000 : 0x40190000), 0);  // 1.25, 3.75, 6.25
-            const bool m_left = (b & kBitLeft) != 0, m_right = (b & kBitRight) != 0;  // never both
-            double inc = 0.0;
-            dmov_if(m_left, inc, C.k30dt); dmov_if(m_right, inc, -C.k30dt);
-            c.steer[a] = dadd(c.steer[a], inc);  // + 0.0 is the identity on every value steer can hold
-            const bool reached = (m_left && c.py[a] <= ty) || (m_right && c.py[a] >= ty);
-            dset_if(reached, c.steer[a], 0.0);
-            if (reached) b &= ~(kBitLeft | kBitRight);
-        }
-        double ang = 0.0;
-        if (c.steer[a] != 0.0) ang = angular_velocity<EXACT>(c.vx[a], c.steer[a]);
-        if (!CONT) c.vy[a] = ang;  // agent.py:144: velocity.y = angular_velocity (discrete update only)
-        dmov_if(L == a, lv, c.vx[a]);
-        const double vdt = dmul(c.vx[a], dt);
-        double px = dadd(c.px[a], vdt);
-        double py = dadd(c.py[a], dmul(c.vy[a], dt));
-        if (CONT) py = dsub(py, dmul(ang, dt));
-        else      py = dsub(py, dmul(dmul(dmul(ang, kRad2Deg), dt), dt));
-        px = dsub(px, dmul(lv, dt));
-        dset_if(L == a, px, 10.0);
-        dset_if(7.0 < py, py, 7.0);   // if y < 1: y = 1 elif y > 6: y = min(y, 7)
-        dset_if(py < 1.0, py, 1.0);
-        c.rx[a] = dadd(c.rx[a], vdt);
-        c.px[a] = px; c.py[a] = py;
-        if (CONT) {
-            const double d0 = fabs(dsub(py, 1.25)), d1 = fabs(dsub(py, 3.75)), d2 = fabs(dsub(py, 6.25));
-            b = tpe_with_lane(b, (d0 <= d1 && d0 <= d2) ? 1 : (d1 <= d2) ? 2 : 3);
-        }
-        c.b[a] = b;
-    }
-    const double lvdt = dmul(lv, dt);  // last tick's leader, this tick's velocity
-
-    // ---- leader / last election: stable sort of the cars by x, descending (highway_core.py:294-297).  In the reference it follows
-    //      the obstacle updates, but it only reads the cars, which are final by now ----
-    int lead = 0, last = 0;
-    double plead = c.px[0], plast = c.px[0], lead_rx = c.rx[0], last_rx = c.rx[0];
-#pragma unroll
-    for (int j = 1; j < A; ++j) {
-        const bool up = c.px[j] > plead, dn = c.px[j] <= plast;  // first of the maxima, last of the minima
-        lead = up ? j : lead; dmov_if(up, plead, c.px[j]); dmov_if(up, lead_rx, c.rx[j]);
-        last = dn ? j : last; dmov_if(dn, plast, c.px[j]); dmov_if(dn, last_rx, c.rx[j]);
-    }
-    h.leader = (uint32_t)lead;
-    (void)last;
-
-    // ---- obstacle updates (agent.py:223-260): yield to the nearest car ahead in the lane, by raw x; the slot is tested for a
-    //      spawn / retire while its values are in registers ----
-    const double thr = dsub(dsub(-2.375, plead), 2.0);
-    const uint32_t newest_mask = (1u << h.newest[0]) | (1u << h.newest[1]) | (1u << h.newest[2]);  // 31 = retired: matches no slot
-    bool want = false;
-    for (int k = 0; k < (int)h.nobs; ++k) {
-        const int lane = ob_lane(h, k);
-        const double orx = ob(k, O_RX), iv = ob(k, O_IV);
-        double bd = tpe_inf(), bv = iv;
-#pragma unroll
-        for (int j = 0; j < A; ++j) {
-            const double d = dsub(c.rx[j], orx);
-            const bool take = (tpe_lane(c.b[j]) == lane) & (orx < c.rx[j]) & (d < bd);  // first wins ties
-            dmov_if(take, bd, d); dmov_if(take, bv, c.vx[j]);
-        }
-        double v = py_clamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
-        dmov_if(bd < tpe_inf(), v, iv);        // else min(init_vx, that car's vx)
-        dmov_if(bv < iv, v, bv);
-        const double odt = dmul(v, dt);
-        const double opx = dsub(dadd(ob(k, O_PX), odt), lvdt);
-        const double orx2 = dadd(orx, odt);
-        ob(k, O_VX) = v; ob(k, O_PX) = opx; ob(k, O_RX) = orx2;
-        want = want | ((((newest_mask >> k) & 1u) != 0u) & (opx < -2.375)) | (dsub(orx2, last_rx) < thr);
-    }
-    h.ofresh = 0;  // every live obstacle has now written its rect
-    if (inf_obs && want) tpe_spawn_retire(h, ob, K, plead, lead_rx, last_rx, seed, env_id);
-
-    // ---- Scenario.rewards -> check_collisions, after the updates and spawns of this tick (highway_core.py:401-422) ----
     int ax75[A], ay37[A];
 #pragma unroll
     for (int a = 0; a < A; ++a) { ax75[a] = rect_x(c.px[a]) + 75; ay37[a] = rect_y(c.py[a]) + 37; }
@@ -292,6 +147,206 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         }
     }
     h.nc_obs += (uint32_t)no; h.nc_agent += (uint32_t)na;
+    return hit;
+}
+
+// The per-tick overlap FILTER works on rects packed into one word, x in the upper and y in the lower 16 bits.  With
+// dx = ax - bx + 75 and dy = ay - by + 37, A overlaps B iff 0 <= dx <= 150 and 0 <= dy <= 74.  Adding 105 to dx and 53 to dy makes
+// both upper bounds 2^k - 1 (255, 127), so T = ((dx + 105) << 16) + (dy + 53) has no bit under the mask 0xFF00FF80 iff both hold:
+// a negative dy borrows into its own high bits (and decrements dx, which then fails or stays valid - dy has failed already), a
+// negative or large dx sets bits above its low eight.  (Fields cannot alias while |dx| < 65 000 px, i.e. within 2 000 m: an
+// episode moves a vehicle by 1 200 m at most.)  min() over the masked words of all pairs is zero iff some pair overlaps.
+constexpr uint32_t kRectMask = 0xFF00FF80u;
+constexpr uint32_t kRectBias = (105u << 16) + 53u;
+__device__ __forceinline__ uint32_t tpe_pack_rect(int x, int y) { return ((uint32_t)x << 16) + (uint32_t)y; }
+
+// one world.act() followed by Scenario.rewards() (highway_core.py:245-399, simple_base.py:65-80); returns the cars that collided
+template <int A, bool CONT, bool EXACT>
+__device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const TpeOb ob, const int K, const MaConsts &C, const double dt,
+                                             const bool inf_obs, const uint32_t (&amask)[A], const double (&a0)[A], const double (&a1)[A],
+                                             const uint64_t seed, const uint64_t env_id, uint32_t &done)
+{
+    h.tick += 1;
+    if (h.tick >= (uint32_t)C.timeout_tick) done |= (1u << A) - 1u;  // highway_core.py:276-277
+
+    // ---- actions for every car in id order (highway_core.py:280-281, :110-188): maintain() of car a sees the lanes the cars
+    //      before it have just switched to and the old lanes of the cars after it - program order ----
+    const uint32_t live = live_mask(h.nobs);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        if (CONT) {
+            c.acc[a] = py_clamp(dadd(c.acc[a], a0[a]), -5.0, 5.0);
+            c.steer[a] = py_clamp(dadd(c.steer[a], a1[a]), -30.0, 30.0);
+            continue;
+        }
+        // amask = the mode bit the action asks for; it fires when not yet set.  The two modes of a pair exclude each other, so
+        // setting the bit and clearing its partner is the identity when nothing fires.
+        const uint32_t am = amask[a];
+        const uint32_t apair = am | ((am & (kBitLeft | kBitDoAcc)) << 1) | ((am & (kBitRight | kBitDoMaint)) >> 1);
+        const uint32_t fire = am & ~c.b[a];
+        c.b[a] = (c.b[a] & ~apair) | am;
+        if (fire & kBitDoMaint) {
+            // all_obstacles iterates the cars (id order) and then the obstacles (insertion order): nearest strictly ahead in the lane,
+            // first wins ties
+            const int lane = c.ln[a];
+            double bpx = tpe_inf(), bvx = c.vx[a];
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+                if (j == a) continue;
+                const bool take = (c.ln[j] == lane) & (c.px[j] > c.px[a]) & (c.px[j] < bpx);
+                dmov_if(take, bpx, c.px[j]); dmov_if(take, bvx, c.vx[j]);
+            }
+            const uint32_t diff = h.olane ^ ((uint32_t)lane * 0x55555555u);
+            uint32_t same = ~(diff | (diff >> 1)) & 0x55555555u & live;
+            while (same) {
+                const int k = (__ffs((int)same) - 1) >> 1;
+                same &= same - 1u;
+                const double opx = ob(k, O_PX), ovx = ob(k, O_VX);
+                const bool take = (opx > c.px[a]) & (opx < bpx);
+                dmov_if(take, bpx, opx); dmov_if(take, bvx, ovx);
+            }
+            c.cruise[a] = bvx;
+        }
+        const int dl = (int)((fire >> 19) & 1u) - (int)((fire >> 18) & 1u);  // RIGHT +1, LEFT -1, only when it fires
+        c.ln[a] = min(max(c.ln[a] + dl, 1), 3);
+        c.acc[a] = py_clamp(c.acc[a], -5.0, 5.0);
+        c.steer[a] = py_clamp(c.steer[a], -30.0, 30.0);
+    }
+
+    // ---- car updates in id order against last tick's leader (agent.py:79-165): a car subtracts the leader's velocity "as it is
+    //      now" (agent.py:147-151) - its new value for the cars after it in id order, its old one for those before ----
+    // Written as three passes over the cars (velocity and steering, angular velocity, position), each a straight line of A
+    // independent dependency chains: the instruction-level parallelism that 12 warps per SM need.
+    const int L = (int)h.leader;
+    double lv_old = c.vx[0];
+#pragma unroll
+    for (int j = 1; j < A; ++j) dmov_if(L == j, lv_old, c.vx[j]);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        uint32_t b = c.b[a];
+        if (!CONT) {
+            const bool m_acc = (b & kBitDoAcc) != 0, m_maint = (b & kBitDoMaint) != 0;  // never both
+            double acc_a = dadd(c.acc[a], dt);
+            dset_if(c.acc[a] < 0.0, acc_a, 0.0);
+            const double vc = ceil(c.vx[a]), cc = ceil(c.cruise[a]);
+            const bool snap = m_maint && vc == cc;
+            const double acc_m = __hiloint2double(snap ? 0 : ((vc <= cc) ? 0x40140000 : (int)0xC0140000), 0);  // 0.0, 5.0, -5.0
+            dmov_if_nz(b & kBitDoAcc, c.acc[a], acc_a);
+            dmov_if_nz(b & kBitDoMaint, c.acc[a], acc_m);
+            dmov_if(snap, c.vx[a], c.cruise[a]);
+            if (m_acc && c.acc[a] == 5.0) b &= ~kBitDoAcc;
+            if (snap) b &= ~kBitDoMaint;
+        }
+        c.vx[a] = py_clamp(dadd(c.vx[a], dmul(c.acc[a], dt)), 0.0, 20.0);
+        if (!CONT) {
+            const double ty = __fma_rn((double)c.ln[a], 2.5, -1.25);  // lane 1, 2, 3: 1.25, 3.75, 6.25 (exact)
+            const bool m_left = (b & kBitLeft) != 0, m_right = (b & kBitRight) != 0;  // never both
+            double inc = 0.0;
+            dmov_if(m_left, inc, C.k30dt); dmov_if(m_right, inc, -C.k30dt);
+            c.steer[a] = dadd(c.steer[a], inc);  // + 0.0 is the identity on every value steer can hold
+            const bool reached = (m_left && c.py[a] <= ty) || (m_right && c.py[a] >= ty);
+            dset_if(reached, c.steer[a], 0.0);
+            if (reached) b &= ~(kBitLeft | kBitRight);
+        }
+        c.b[a] = b;
+    }
+    double lv = c.vx[0];  // the leader's velocity "as it is now" for the cars after it: its new value
+#pragma unroll
+    for (int j = 1; j < A; ++j) dmov_if(L == j, lv, c.vx[j]);
+    double ang[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        // evaluated unconditionally (tan(0) = 0 gives 0 as well; a division by 4 / tan(0) = inf gives 0): no branch between the cars
+        ang[a] = angular_velocity<EXACT>(c.vx[a], c.steer[a]);
+        dset_if(!(c.steer[a] != 0.0), ang[a], 0.0);
+        if (!CONT) c.vy[a] = ang[a];  // agent.py:144: velocity.y = angular_velocity (discrete update only)
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        double lva = lv_old;
+        dmov_if(L < a, lva, lv);
+        const double vdt = dmul(c.vx[a], dt);
+        double px = dadd(c.px[a], vdt);
+        double py = dadd(c.py[a], dmul(c.vy[a], dt));
+        if (CONT) py = dsub(py, dmul(ang[a], dt));
+        else      py = dsub(py, dmul(dmul(dmul(ang[a], kRad2Deg), dt), dt));
+        px = dsub(px, dmul(lva, dt));
+        dset_if(L == a, px, 10.0);
+        dset_if(7.0 < py, py, 7.0);   // if y < 1: y = 1 elif y > 6: y = min(y, 7)
+        dset_if(py < 1.0, py, 1.0);
+        c.rx[a] = dadd(c.rx[a], vdt);
+        c.px[a] = px; c.py[a] = py;
+        if (CONT) {
+            const double d0 = fabs(dsub(py, 1.25)), d1 = fabs(dsub(py, 3.75)), d2 = fabs(dsub(py, 6.25));
+            c.ln[a] = (d0 <= d1 && d0 <= d2) ? 1 : (d1 <= d2) ? 2 : 3;
+        }
+    }
+    const double lvdt = dmul(lv, dt);  // last tick's leader, this tick's velocity
+
+    // ---- leader / last election: stable sort of the cars by x, descending (highway_core.py:294-297).  In the reference it follows
+    //      the obstacle updates, but it only reads the cars, which are final by now ----
+    int lead = 0;
+    double plead = c.px[0], plast = c.px[0], lead_rx = c.rx[0], last_rx = c.rx[0];
+#pragma unroll
+    for (int j = 1; j < A; ++j) {
+        const bool up = c.px[j] > plead, dn = c.px[j] <= plast;  // first of the maxima, last of the minima
+        lead = up ? j : lead; dmov_if(up, plead, c.px[j]); dmov_if(up, lead_rx, c.rx[j]);
+        dmov_if(dn, plast, c.px[j]); dmov_if(dn, last_rx, c.rx[j]);
+    }
+    h.leader = (uint32_t)lead;
+
+    // the cars' rects for check_collisions (highway_core.py:401-422), packed for the overlap filter (see kRectMask)
+    uint32_t pa[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) pa[a] = tpe_pack_rect(rect_x(c.px[a]) + 75, rect_y(c.py[a]) + 37);
+    uint32_t nohit = kRectMask;  // min over all rect pairs of the masked test word: 0 = some pair overlaps -> the exact count runs (rare)
+
+    // ---- obstacle updates (agent.py:223-260): yield to the nearest car ahead in the lane, by raw x.  While a slot's new values
+    //      are in registers it is tested for a spawn / retire and against the cars' rects (an obstacle that is retired below is
+    //      more than 14 m behind the last car, so testing it too cannot add an overlap in a consistent frame; the exact count
+    //      walks the final list in any case) ----
+    const double thr = dsub(dsub(-2.375, plead), 2.0);
+    const uint32_t newest_mask = (1u << h.newest[0]) | (1u << h.newest[1]) | (1u << h.newest[2]);  // 31 = retired: matches no slot
+    bool want = false;
+    for (int k = 0; k < (int)h.nobs; ++k) {
+        const int lane = ob_lane(h, k);
+        const double orx = ob(k, O_RX), iv = ob(k, O_IV);
+        double bd = tpe_inf(), bv = iv;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            const double d = dsub(c.rx[j], orx);
+            const bool take = (c.ln[j] == lane) & (orx < c.rx[j]) & (d < bd);  // first wins ties
+            dmov_if(take, bd, d); dmov_if(take, bv, c.vx[j]);
+        }
+        double v = py_clamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
+        dmov_if(bd < tpe_inf(), v, iv);        // else min(init_vx, that car's vx)
+        dmov_if(bv < iv, v, bv);
+        const double odt = dmul(v, dt);
+        const double opx = dsub(dadd(ob(k, O_PX), odt), lvdt);
+        const double orx2 = dadd(orx, odt);
+        ob(k, O_VX) = v; ob(k, O_PX) = opx; ob(k, O_RX) = orx2;
+        want = want | ((((newest_mask >> k) & 1u) != 0u) & (opx < -2.375)) | (dsub(orx2, last_rx) < thr);
+        const uint32_t pb = tpe_pack_rect(rect_x(opx), 80 * lane - 59) - kRectBias;  // y = 21 + 80 * (lane - 1)
+#pragma unroll
+        for (int a = 0; a < A; ++a) nohit = min(nohit, (pa[a] - pb) & kRectMask);
+    }
+    h.ofresh = 0;  // every live obstacle has now written its rect
+    if (inf_obs && want) {
+        tpe_spawn_retire(h, ob, K, plead, lead_rx, last_rx, seed, env_id);
+        if (h.ofresh) {  // a slot spawned in this tick carries pygame's default rect (0, 0, 76, 38) into check_collisions
+#pragma unroll
+            for (int a = 0; a < A; ++a) nohit = min(nohit, (pa[a] + kRectBias) & kRectMask);
+        }
+    }
+
+    // ---- Scenario.rewards -> check_collisions, after the updates and spawns of this tick (highway_core.py:401-422) ----
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+#pragma unroll
+        for (int j = a + 1; j < A; ++j) nohit = min(nohit, (pa[a] - pa[j] + (tpe_pack_rect(75, 37) + kRectBias)) & kRectMask);
+    }
+    uint32_t hit = 0;
+    if (nohit == 0u) hit = tpe_collide_exact<A>(h, c, ob);
     done |= hit;
     return hit;
 }
@@ -397,7 +452,8 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
             const float *p = S.cars + (int64_t)(a * 9) * n + i;
             c.px[a] = (double)p[0]; c.py[a] = (double)p[n]; c.rx[a] = (double)p[2 * n]; c.vx[a] = (double)p[3 * n]; c.vy[a] = (double)p[4 * n];
             c.acc[a] = (double)p[5 * n]; c.steer[a] = (double)p[6 * n]; c.cruise[a] = (double)p[7 * n];
-            c.b[a] = __float_as_uint(p[8 * n]);
+            const uint32_t w = __float_as_uint(p[8 * n]);
+            c.b[a] = w & ~(3u << HW_BITS_LANE_SHIFT); c.ln[a] = tpe_lane(w);
         }
         for (int k = 0; k < (int)h.nobs; ++k) {
             const float4 o = S.obst[(int64_t)k * n + i];
@@ -464,7 +520,7 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
             float *p = S.cars + (int64_t)(a * 9) * n + i;
             p[0] = (float)c.px[a]; p[n] = (float)c.py[a]; p[2 * n] = (float)c.rx[a]; p[3 * n] = (float)c.vx[a]; p[4 * n] = (float)c.vy[a];
             p[5 * n] = (float)c.acc[a]; p[6 * n] = (float)c.steer[a]; p[7 * n] = (float)c.cruise[a];
-            p[8 * n] = __uint_as_float(c.b[a]);
+            p[8 * n] = __uint_as_float(tpe_with_lane(c.b[a], c.ln[a]));
         }
         for (int k = 0; k < (int)h.nobs; ++k)
             S.obst[(int64_t)k * n + i] = make_float4((float)ob(k, O_PX), (float)ob(k, O_RX), (float)ob(k, O_VX), (float)ob(k, O_IV));
@@ -488,10 +544,12 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
             }
         }
         __syncwarp();
-        const int per_env = cn * D2;
+        const int per_env = cn * D2;                  // compile-time after unrolling: the division below is a multiply and a shift
+        const int nv = (n - i0 < 32) ? (int)(n - i0) : 32;   // environments of this warp that exist
+        float2 *dst = out2 + i0 * (int64_t)(A * D2) + c0 * D2;
         for (int idx = lane_id; idx < 32 * per_env; idx += 32) {
             const int e = idx / per_env, q = idx - e * per_env;
-            if (i0 + e < n) out2[(i0 + e) * (int64_t)(A * D2) + c0 * D2 + q] = stage[idx];
+            if (e < nv) dst[e * (A * D2) + q] = stage[idx];
         }
     }
 
