@@ -257,7 +257,9 @@ def side_measure(kind, continuous, n, dev, rank, args, steps=100, warmup=5, agen
         st = env.episode_statistics()
         out.update({"agents": A, "agent_steps_per_s": A * n / t, "mean_live_obstacles": live,
                     "live_slot_bytes_per_env_step": b_live, "roofline_frac_live_slots": n * b_live / t / 1e9 / peak,
-                    "dropped_spawns": st.get("dropped_spawns"), "mean_episode_length": st.get("mean_length")})
+                    "dropped_spawns": st.get("dropped_spawns"), "mean_episode_length": st.get("mean_length"),
+                    "kernel": "ma_tpe_step_kernel (thread per environment, cars in registers)" if n >= 65536
+                              else "ma_grp_step_kernel (lane per car)"})
     del env, acts, fb
     torch.cuda.empty_cache()
     return out
@@ -295,6 +297,59 @@ def rollout_measure(dev, rank, world, envs=131072, nsteps=240, rollouts=3):
            "rollout_env_steps_per_s": world * envs * nsteps * rollouts / (ms * 1e-3), "ms_per_rollout": ms / rollouts,
            "us_per_step": 1e3 * ms / rollouts / nsteps, "episodes_last_rollout": stats["episodes"]}
     del run, env, pol
+    torch.cuda.empty_cache()
+    return out
+
+
+def consumers_measure(dev, rank):
+    """SURVEY.md section 8(f) consumers on the device, one GPU: a2c's 5-step rollouts (DeviceA2CRunner, one CUDA graph per
+    rollout), ppo2-style collection over the multi-agent env (DeviceRunner, every car a row of the shared policy), and the
+    MADDPG rollout loop's transition store (MADeviceCollector: env step + hw_ring_store + hw_obs_moments)"""
+    import torch
+    from gym_highway_b200 import HighwayMAVecEnv, HighwayVecEnv
+    from gym_highway_b200.replay import MADeviceCollector, RingMemory, RunningMeanStd
+    from gym_highway_b200.rollout import DeviceA2CRunner, DeviceRunner, MlpPolicy
+    torch.manual_seed(0)
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize(dev)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(reps):
+            fn()
+        t1.record()
+        torch.cuda.synchronize(dev)
+        return t0.elapsed_time(t1) * 1e-3 / reps
+
+    n, T = 131072, 5
+    run = DeviceA2CRunner(HighwayVecEnv(n, seed=0, device=dev, env_id0=rank * n), MlpPolicy(18, 4, bf16_inference=True).to(dev), nsteps=T, seed=0)
+    t = timed(run.run_graphed, 100)
+    out["a2c_rollout"] = {"workload": "a2c runner: %d single-agent envs, nsteps=%d, MLP 18-256-256-256 (bf16), fused sampling, step_into, "
+                                      "hw_nstep_returns, one CUDA graph per rollout" % (n, T),
+                          "rollout_env_steps_per_s": n * T / t, "us_per_step": 1e6 * t / T}
+    del run
+    n, A, T = 32768, 5, 64
+    run = DeviceRunner(HighwayMAVecEnv(n, num_agents=A, seed=0, device=dev, env_id0=rank * n), MlpPolicy(4 * A + 14, 4, bf16_inference=True).to(dev),
+                       nsteps=T, seed=0)
+    t = timed(run.run_graphed, 5)
+    out["ma_ppo2_rollout"] = {"workload": "ppo2-style collection over the multi-agent env: %d envs x %d cars (every car a row of the shared "
+                                          "MLP 34-256-256-256), T=%d, one CUDA graph per rollout" % (n, A, T),
+                              "rollout_env_steps_per_s": n * T / t, "agent_steps_per_s": n * A * T / t, "us_per_step": 1e6 * t / T}
+    del run
+    n, A, T = 65536, 5, 20
+    env = HighwayMAVecEnv(n, num_agents=A, continuous=True, seed=0, device=dev, env_id0=rank * n)
+    mem = RingMemory(n * 12, A, env.obs_dim, 2, device=dev)
+    rms = RunningMeanStd(shape=(A, env.obs_dim), device=dev)
+    actor = torch.nn.Sequential(torch.nn.Linear(env.obs_dim, 64), torch.nn.ReLU(), torch.nn.Linear(64, 2), torch.nn.Tanh()).to(dev)
+    col = MADeviceCollector(env, lambda obs: actor(obs.reshape(-1, env.obs_dim)), mem, obs_rms=rms)
+    t = timed(lambda: col.collect(T), 3)
+    out["maddpg_collection"] = {"workload": "MADDPG rollout loop: %d multi-agent envs x %d cars (continuous), torch actor 34-64-2, env step_into, "
+                                            "hw_ring_store into a %d-row ring, hw_obs_moments; eager launches" % (n, A, mem.limit),
+                                "transitions_per_s": n * T / t, "agent_transitions_per_s": n * A * T / t, "us_per_step": 1e6 * t / T,
+                                "ring_wrapped": mem.nb_entries == mem.limit}
+    del col, mem, env, rms
     torch.cuda.empty_cache()
     return out
 
@@ -387,6 +442,8 @@ def main():
             "continuous_262144": side_measure("ma", True, 262144, dev, rank, args, steps=60, warmup=5)}
     if not args.no_extras and info["kind"] == "sa" and not info["continuous"]:
         extras["configs3"] = rollout_measure(dev, rank, world)
+    if not args.no_extras and world == 1 and info["kind"] == "sa" and not info["continuous"] and n != 65536:
+        extras["consumers"] = consumers_measure(dev, rank)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -411,7 +468,7 @@ def main():
                        "parallelism": "independent env shards, %d rank(s), no data-path collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(info["kind"], info["continuous"], n), "peak_source": peak_src,
-                         "kernel": "sa_step_kernel" if info["kind"] == "sa" else "ma_grp_step_kernel",
+                         "kernel": "sa_step_kernel" if info["kind"] == "sa" else ("ma_tpe_step_kernel" if n >= 65536 else "ma_grp_step_kernel"),
                          "algorithmic_bytes_per_env_step": bps,
                          "avg_launch_us": avg_launch_s * 1e6, "min_launch_us": float(dev_ms.min()) * 1e3},
             "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,

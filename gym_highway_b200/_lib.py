@@ -17,6 +17,7 @@ FLAG_NO_AUTORESET = 4
 FLAG_SHARED_REWARD = 16
 FLAG_EXACT_STEERING = 32
 FLAG_MA_THREAD_PER_ENV = 64
+FLAG_MA_LANE_PER_CAR = 128
 MA_MAX_AGENTS = 5
 MA_MAX_SLOTS = 16
 

@@ -29,7 +29,10 @@ namespace hw {
 #define HW_TPE_MIN_BLOCKS 3
 #endif
 constexpr int kTpeBlock = HW_TPE_BLOCK;
-constexpr int kTpeWarpDoubles = kMaxK * O_NF * 32;  // one warp's obstacle region: 16 KB
+#ifndef HW_TPE_SLOTS
+#define HW_TPE_SLOTS kMaxK
+#endif
+constexpr int kTpeWarpDoubles = HW_TPE_SLOTS * O_NF * 32;  // one warp's obstacle region: 16 KB for 16 slots
 
 struct TpeOb {  // this thread's column of the warp-private obstacle region
     double *base;

@@ -28,7 +28,7 @@ class HighwayMAVecEnv(VecEnv):
 
     def __init__(self, num_envs, num_agents=5, continuous=False, seed=0, device=None, world_config=None,
                  shared_reward=False, num_slots=_lib.MA_MAX_SLOTS, env_id0=0, return_numpy=False, auto_reset=True,
-                 track_stats=True, exact_steering=False, kernel="group"):
+                 track_stats=True, exact_steering=False, kernel="auto"):
         cfg = dict(manual=False, inf_obs=True, save=False, render=False, real_time=False)
         cfg.update(world_config or {})
         if cfg['manual'] or cfg['save'] or cfg['render']:
@@ -51,9 +51,11 @@ class HighwayMAVecEnv(VecEnv):
         self._flags = ((_lib.FLAG_CONTINUOUS if continuous else 0) | (0 if cfg['inf_obs'] else _lib.FLAG_NO_INF_OBS)
                        | (0 if auto_reset else _lib.FLAG_NO_AUTORESET) | (_lib.FLAG_SHARED_REWARD if shared_reward else 0)
                        | (_lib.FLAG_EXACT_STEERING if exact_steering else 0)
-                       | (_lib.FLAG_MA_THREAD_PER_ENV if kernel == "thread" else 0))
-        if kernel not in ("group", "thread"):
-            raise ValueError("kernel must be 'group' (eight lanes per environment, default) or 'thread' (one thread per environment)")
+                       | (_lib.FLAG_MA_THREAD_PER_ENV if kernel == "thread" else 0)
+                       | (_lib.FLAG_MA_LANE_PER_CAR if kernel == "group" else 0))
+        if kernel not in ("auto", "group", "thread"):
+            raise ValueError("kernel must be 'auto' (chosen by batch size, default), 'group' (a lane per car) or 'thread' (a thread per "
+                             "environment, cars in registers); the results are identical")
         self._seed = int(seed) & (2 ** 64 - 1)
         self._env_id0 = int(env_id0)
         A, K = self.num_agents, self.num_slots

@@ -43,8 +43,12 @@ extern "C" {
 #define HW_FLAG_SHARED_REWARD 16 /* multi-agent: every car receives the sum of the rewards (shared_reward=True) */
 #define HW_FLAG_EXACT_STEERING 32 /* evaluate vx / (4 / tan) with the reference's two divisions instead of vx*tan/4
                                     * (slower; floats then match the fp64 reference bit for bit after fp32 rounding) */
-#define HW_FLAG_MA_THREAD_PER_ENV 64 /* multi-agent step: use the one-thread-per-environment kernel instead of the default
-                                      * eight-lanes-per-environment kernel (same results; kept for comparison) */
+#define HW_FLAG_MA_THREAD_PER_ENV 64  /* multi-agent step: force the one-thread-per-environment kernel (cars in registers, hw_ma_tpe.cu) */
+#define HW_FLAG_MA_LANE_PER_CAR  128  /* multi-agent step: force the lane-per-car kernel (hw_ma_grp.cu).  Neither flag: chosen by batch
+                                       * size - the thread-per-environment kernel from HW_MA_TPE_MIN_ENVS environments up (fewer
+                                       * instructions per environment), the lane-per-car kernel below (five times the threads for a
+                                       * batch that cannot fill the GPU otherwise).  Same results either way. */
+#define HW_MA_TPE_MIN_ENVS 65536
 
 /* discrete actions, gym_highway/envs/highway_env.py:14-20 */
 #define HW_ACT_LEFT 0

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gym_highway_b200 import HighwayMAVecEnv
 
-def probe(n, A=5, cont=False, steps=40, kernel=os.environ.get('HW_MA_KERNEL', 'group')):
+def probe(n, A=5, cont=False, steps=40, kernel=os.environ.get('HW_MA_KERNEL', 'auto')):
     env = HighwayMAVecEnv(n, num_agents=A, continuous=cont, seed=0, kernel=kernel, exact_steering=bool(int(os.environ.get('HW_EXACT', '0'))))
     g = torch.Generator(device='cuda'); g.manual_seed(1)
     acts = (torch.rand((8, n, A, 2), generator=g, device='cuda') * 2 - 1) if cont else torch.randint(0, 4, (8, n, A), generator=g, device='cuda', dtype=torch.int32)

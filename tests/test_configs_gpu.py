@@ -99,11 +99,12 @@ def test_configs1_65536_envs_default_mode_within_contract():
     assert nbits <= 1e-5 * nvals, "%d of %d float values differ in the last bit" % (nbits, nvals)
 
 
+@pytest.mark.parametrize("kernel", ["group", "thread"])
 @pytest.mark.parametrize("continuous", [False, True])
-def test_configs2_16384_ma_envs_uniform_random_actions(continuous):
+def test_configs2_16384_ma_envs_uniform_random_actions(continuous, kernel):
     from gym_highway_b200 import HighwayMAVecEnv
     n, A, steps, seed, id0, calm = 16384, 5, 320 if not continuous else 150, 12, 5000, 1024
-    env = HighwayMAVecEnv(n, num_agents=A, continuous=continuous, seed=seed, env_id0=id0, exact_steering=True)
+    env = HighwayMAVecEnv(n, num_agents=A, continuous=continuous, seed=seed, env_id0=id0, exact_steering=True, kernel=kernel)
     st = mo.MaState(n, A)
     mo.ma_reset(st)
     rng = np.random.RandomState(23)
