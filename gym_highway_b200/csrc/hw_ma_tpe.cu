@@ -78,11 +78,21 @@ __device__ __forceinline__ void tpe_reset(MaHead &h, TpeCars<A> &c, const TpeOb 
 
 // spawn (the lane's newest obstacle has fallen behind x = -2.375: highway_core.py:300-323, the old obstacle stays and is slowed
 // down) and retire (what the last car has cleared: :327-342, order preserving compaction).  Rare; kept out of line.
-__device__ __forceinline__ void tpe_spawn_retire(MaHead &h, const TpeOb ob, const int K, const double plead, const double lead_rx,
-                                                     const double last_rx, const uint64_t seed, const uint64_t env_id)
+struct TpeSlots {  // the header words spawn / retire change, passed and returned by value (registers) across the out-of-line call
+    uint32_t nobs, olane, ofresh, n0, n1, n2, spawn_ctr, flags;
+};
+
+#ifndef HW_TPE_RARE_ATTR
+#define HW_TPE_RARE_ATTR __noinline__
+#endif
+static __device__ HW_TPE_RARE_ATTR TpeSlots tpe_spawn_retire(TpeSlots h, double *ob_base, const int K, const double plead, const double lead_rx,
+                                                            const double last_rx, const uint64_t seed, const uint64_t env_id)
 {
+    const TpeOb ob{ob_base};
+    uint32_t newest[3] = {h.n0, h.n1, h.n2};
+#pragma unroll
     for (int lane = 0; lane < 3; ++lane) {
-        const uint32_t s = h.newest[lane];
+        const uint32_t s = newest[lane];
         if (s >= 31u) continue;  // the lane's newest obstacle was retired: the reference never spawns there again
         if (ob((int)s, O_PX) < -2.375) {
             double u1, u2;
@@ -98,7 +108,7 @@ __device__ __forceinline__ void tpe_spawn_retire(MaHead &h, const TpeOb ob, cons
                 ob(nk, O_VX) = v; ob(nk, O_IV) = v;
                 h.olane = (h.olane & ~(3u << (2 * nk))) | ((uint32_t)(lane + 1) << (2 * nk));
                 h.ofresh |= 1u << nk;
-                h.newest[lane] = (uint32_t)nk;
+                newest[lane] = (uint32_t)nk;
                 h.nobs += 1;
             } else {
                 h.flags |= 1u;  // out of slots: the spawn is dropped (tests require this never to happen)
@@ -111,14 +121,15 @@ __device__ __forceinline__ void tpe_spawn_retire(MaHead &h, const TpeOb ob, cons
     for (int k = 0; k < (int)h.nobs; ++k) {
         if (dsub(ob(k, O_RX), last_rx) < thr) continue;
         if (w != k) { ob(w, O_PX) = ob(k, O_PX); ob(w, O_RX) = ob(k, O_RX); ob(w, O_VX) = ob(k, O_VX); ob(w, O_IV) = ob(k, O_IV); }
-        nl |= (uint32_t)ob_lane(h, k) << (2 * w);
+        nl |= ((h.olane >> (2 * k)) & 3u) << (2 * w);
         nf |= ((h.ofresh >> k) & 1u) << w;
-        if (h.newest[0] == (uint32_t)k) nn0 = (uint32_t)w;
-        if (h.newest[1] == (uint32_t)k) nn1 = (uint32_t)w;
-        if (h.newest[2] == (uint32_t)k) nn2 = (uint32_t)w;
+        if (newest[0] == (uint32_t)k) nn0 = (uint32_t)w;
+        if (newest[1] == (uint32_t)k) nn1 = (uint32_t)w;
+        if (newest[2] == (uint32_t)k) nn2 = (uint32_t)w;
         ++w;
     }
-    h.nobs = (uint32_t)w; h.olane = nl; h.ofresh = nf; h.newest[0] = nn0; h.newest[1] = nn1; h.newest[2] = nn2;
+    h.nobs = (uint32_t)w; h.olane = nl; h.ofresh = nf; h.n0 = nn0; h.n1 = nn1; h.n2 = nn2;
+    return h;
 }
 
 // exact check_collisions over the current obstacle list (fresh slots carry pygame's default rect) and the other cars: counters,
@@ -335,7 +346,10 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
     }
     h.ofresh = 0;  // every live obstacle has now written its rect
     if (inf_obs && want) {
-        tpe_spawn_retire(h, ob, K, plead, lead_rx, last_rx, seed, env_id);
+        const TpeSlots r = tpe_spawn_retire(TpeSlots{h.nobs, h.olane, h.ofresh, h.newest[0], h.newest[1], h.newest[2], h.spawn_ctr, h.flags},
+                                            ob.base, K, plead, lead_rx, last_rx, seed, env_id);
+        h.nobs = r.nobs; h.olane = r.olane; h.ofresh = r.ofresh; h.newest[0] = r.n0; h.newest[1] = r.n1; h.newest[2] = r.n2;
+        h.spawn_ctr = r.spawn_ctr; h.flags = r.flags;
         if (h.ofresh) {  // a slot spawned in this tick carries pygame's default rect (0, 0, 76, 38) into check_collisions
 #pragma unroll
             for (int a = 0; a < A; ++a) nohit = min(nohit, (pa[a] + kRectBias) & kRectMask);
