@@ -19,6 +19,7 @@ FLAG_EXACT_STEERING = 32
 FLAG_MA_THREAD_PER_ENV = 64
 FLAG_MA_LANE_PER_CAR = 128
 MA_MAX_AGENTS = 5
+MA_MAX_AGENTS_EXT = 8
 MA_MAX_SLOTS = 16
 
 SA_OBS_DIM = 18

@@ -24,12 +24,12 @@ namespace hw {
 // start grid: simple_base.py:32-43 ("X" formation, three obstacles behind the cars); counters of the episode cleared
 __device__ __forceinline__ void ma_reset_env(MaHead &h, double *sm_car, double *sm_ob, uint32_t *cbits, int A)
 {
-    const double cx[5] = {10.0, 10.0, 7.5, 5.0, 5.0};
-    const int cl[5] = {1, 3, 2, 1, 3};
     for (int a = 0; a < A; ++a) {
-        CAR(a, C_PX) = cx[a]; CAR(a, C_PY) = lane_centre(cl[a] - 1); CAR(a, C_RX) = cx[a];
+        const double cx = ma_start_x(a);
+        const int cl = ma_start_lane(a);
+        CAR(a, C_PX) = cx; CAR(a, C_PY) = lane_centre(cl - 1); CAR(a, C_RX) = cx;
         CAR(a, C_VX) = 0.0; CAR(a, C_VY) = 0.0; CAR(a, C_ACC) = 0.0; CAR(a, C_STEER) = 0.0; CAR(a, C_CRUISE) = 0.0;
-        cbits[a] = (uint32_t)cl[a] << HW_BITS_LANE_SHIFT;
+        cbits[a] = (uint32_t)cl << HW_BITS_LANE_SHIFT;
     }
     const double ox[3] = {-20.0, -25.0, -40.0}, ov[3] = {7.0, 5.0, 6.0};
     for (int k = 0; k < 3; ++k) { OB(k, O_PX) = ox[k]; OB(k, O_RX) = ox[k]; OB(k, O_VX) = ov[k]; OB(k, O_IV) = ov[k]; }
@@ -124,7 +124,7 @@ ma_reset_kernel(MaPtrs S, const uint8_t *__restrict__ mask, float *__restrict__ 
     if (i >= n) return;
     if (mask && !mask[i]) return;
     MaHead h;
-    uint32_t cbits[kMaxA];
+    uint32_t cbits[kMaxAExt];
     ma_load_head(h, S, i, n);  // spawn_ctr survives
     ma_reset_env(h, sm_car, sm_ob, cbits, S.A);
     if (obs) ma_observe(h, sm_car, sm_ob, S.A, obs + i * (int64_t)S.A * (4 * S.A + 14));
@@ -140,7 +140,7 @@ ma_observe_kernel(MaPtrs S, float *__restrict__ obs, const int64_t n)
     const int64_t i = (int64_t)blockIdx.x * kMaBlock + threadIdx.x;
     if (i >= n) return;
     MaHead h;
-    uint32_t cbits[kMaxA];
+    uint32_t cbits[kMaxAExt];
     ma_load(h, sm_car, sm_ob, cbits, S, i, n);
     ma_observe(h, sm_car, sm_ob, S.A, obs + i * (int64_t)S.A * (4 * S.A + 14));
 }
@@ -150,7 +150,7 @@ static inline bool ma_aligned16(const void *p) { return (reinterpret_cast<uintpt
 static int ma_check(const HwMaState *st, int64_t n)
 {
     if (!st || n <= 0 || !st->cars || !st->obst || !st->head) return HW_E_BADARG;
-    if (st->num_agents < 1 || st->num_agents > kMaxA || st->num_slots < 3 || st->num_slots > kMaxK) return HW_E_BADARG;
+    if (st->num_agents < 1 || st->num_agents > kMaxAExt || st->num_slots < 3 || st->num_slots > kMaxK) return HW_E_BADARG;
     if (!ma_aligned16(st->obst)) return HW_E_ALIGN;
     return 0;
 }
@@ -190,7 +190,9 @@ static int ma_launch_step(const HwMaState *st, const void *actions, const HwMaOu
     // two layouts of the same step (identical results): a thread per environment with the cars in registers (hw_ma_tpe.cu: fewest
     // instructions per environment, 313 us against 371 us at 262 144 environments) or a lane per car (hw_ma_grp.cu: five times the
     // threads, the better fit for a batch too small to fill the GPU - 41 us against 53 us at 16 384)
-    const bool tpe = (flags & HW_FLAG_MA_THREAD_PER_ENV) || (!(flags & HW_FLAG_MA_LANE_PER_CAR) && n >= HW_MA_TPE_MIN_ENVS);
+    if (st->num_agents > kMaxA && (flags & HW_FLAG_MA_LANE_PER_CAR)) return HW_E_BADARG;  // the extension (6..8 cars) has one kernel
+    const bool tpe = (flags & HW_FLAG_MA_THREAD_PER_ENV) || st->num_agents > kMaxA
+                     || (!(flags & HW_FLAG_MA_LANE_PER_CAR) && n >= HW_MA_TPE_MIN_ENVS);
     if (tpe) return ma_tpe_launch_step(st, actions, out, C_, seed, env_id0, n, flags, stream);
     return ma_grp_launch_step(st, actions, out, C_, seed, env_id0, n, flags, stream);
 }

@@ -8,6 +8,14 @@ namespace hw {
 
 constexpr int kMaBlock = 64;
 constexpr int kMaxA = HW_MA_MAX_AGENTS;
+constexpr int kMaxAExt = HW_MA_MAX_AGENTS_EXT;
+
+// start grid (simple_base.py:32-38): the "X" formation (10, L1), (10, L3), (7.5, L2), (5, L1), (5, L3); cars 5..7 are the
+// extension beyond the reference's five slots: (2.5, L2), (0, L3), (-2.5, L1) - staggered backwards, and keeping lane 1 clear of
+// x in (-1.2, 3.6): the three start obstacles respawn on the first tick, and a car whose rect covers the pixel origin is hit by
+// their default rects (0, 0, 76, 38) (highway_core.py:314-316 then :407)
+__host__ __device__ __forceinline__ double ma_start_x(int a) { return (a < 2) ? 10.0 : (a == 2) ? 7.5 : (a < 5) ? 5.0 : 7.5 - 2.5 * (a - 3); }
+__host__ __device__ __forceinline__ int ma_start_lane(int a) { return (a == 2 || a == 5) ? 2 : (a == 0 || a == 3 || a == 7) ? 1 : 3; }
 constexpr int kMaxK = HW_MA_MAX_SLOTS;
 
 // car fields in shared memory

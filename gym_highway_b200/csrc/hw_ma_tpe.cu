@@ -61,8 +61,8 @@ __device__ __forceinline__ void tpe_reset(MaHead &h, TpeCars<A> &c, const TpeOb 
 {
 #pragma unroll
     for (int a = 0; a < A; ++a) {
-        const double cx = (a < 2) ? 10.0 : (a == 2) ? 7.5 : 5.0;
-        const int cl = (a == 0 || a == 3) ? 1 : (a == 2) ? 2 : 3;
+        const double cx = ma_start_x(a);
+        const int cl = ma_start_lane(a);
         c.px[a] = cx; c.py[a] = lane_centre(cl - 1); c.rx[a] = cx; c.vx[a] = 0.0; c.vy[a] = 0.0; c.acc[a] = 0.0; c.steer[a] = 0.0; c.cruise[a] = 0.0;
         c.b[a] = 0; c.ln[a] = cl;
     }
@@ -434,7 +434,7 @@ __device__ __forceinline__ void tpe_observe_row(const TpeCars<A> &c, const int a
 }
 
 template <int A, bool CONT, bool EXACT>
-__global__ void __launch_bounds__(kTpeBlock, HW_TPE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTpeBlock, (A <= kMaxA) ? HW_TPE_MIN_BLOCKS : 2)  // the 6..8-car extension needs ~250 registers
 ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew,
                    uint8_t *__restrict__ done_out, double *__restrict__ term, unsigned long long *__restrict__ stats,
                    const MaConsts C, const uint64_t seed, const uint64_t env_id0, const int64_t n, const int flags)
@@ -463,7 +463,7 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
         ma_load_head(h, S, i, n);
         // is_done persists until reset() (highway_core.py:239, :420): with HW_FLAG_NO_AUTORESET a car that finished in an earlier
         // step is still done, and the step then ends after its first tick (highway_env.py:85-86)
-        done = (h.flags >> 8) & 31u; h.flags &= 0xFFu;
+        done = (h.flags >> 8) & 0xFFu; h.flags &= 0xFFu;
 #pragma unroll
         for (int a = 0; a < A; ++a) {
             const float *p = S.cars + (int64_t)(a * 9) * n + i;
@@ -612,6 +612,9 @@ int ma_tpe_launch_step(const HwMaState *st, const void *actions, const HwMaOut *
     case 3: return ma_tpe_launch_a<3>(S, actions, out, C_, seed, env_id0, n, flags, stream);
     case 4: return ma_tpe_launch_a<4>(S, actions, out, C_, seed, env_id0, n, flags, stream);
     case 5: return ma_tpe_launch_a<5>(S, actions, out, C_, seed, env_id0, n, flags, stream);
+    case 6: return ma_tpe_launch_a<6>(S, actions, out, C_, seed, env_id0, n, flags, stream);
+    case 7: return ma_tpe_launch_a<7>(S, actions, out, C_, seed, env_id0, n, flags, stream);
+    case 8: return ma_tpe_launch_a<8>(S, actions, out, C_, seed, env_id0, n, flags, stream);
     }
     return HW_E_BADARG;
 }

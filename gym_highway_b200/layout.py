@@ -81,7 +81,7 @@ def unpack_ma(cars, obst, head, A, K):
                 obst=obst_c, olane=olane, ofresh=ofresh, newest=newest.astype(np.int32),
                 nc_obs=head[4].astype(np.int32), nc_agent=head[5].astype(np.int32), spawn_ctr=head[6].astype(np.uint32),
                 ep_len=head[7].astype(np.int32), ep_ret=ep_ret.copy(), overflow=((head[3] >> 16) & 0xFF).astype(np.int32),
-                done_mask=((head[3] >> 24) & 31).astype(np.int32))
+                done_mask=((head[3] >> 24) & 0xFF).astype(np.int32))
 
 
 def pack_ma(c, A, K):
@@ -107,7 +107,7 @@ def pack_ma(c, A, K):
     head[2] = np.sum(np.where(live, np.asarray(c["olane"]).astype(np.uint32) << (2 * k), 0), axis=1, dtype=np.uint64).astype(np.uint32)
     head[3] = (np.sum(np.where(live, (np.asarray(c["ofresh"]).astype(np.uint32) & 1) << k, 0), axis=1, dtype=np.uint64).astype(np.uint32)
                | ((np.asarray(c.get("overflow", np.zeros(n))).astype(np.uint32) & 0xFF) << 16)
-               | ((np.asarray(c.get("done_mask", np.zeros(n))).astype(np.uint32) & 31) << 24))
+               | ((np.asarray(c.get("done_mask", np.zeros(n))).astype(np.uint32) & 0xFF) << 24))
     head[4] = np.asarray(c["nc_obs"]).astype(np.uint32)
     head[5] = np.asarray(c["nc_agent"]).astype(np.uint32)
     head[6] = np.asarray(c["spawn_ctr"]).astype(np.uint32)

@@ -28,14 +28,20 @@ class HighwayMAVecEnv(VecEnv):
 
     def __init__(self, num_envs, num_agents=5, continuous=False, seed=0, device=None, world_config=None,
                  shared_reward=False, num_slots=_lib.MA_MAX_SLOTS, env_id0=0, return_numpy=False, auto_reset=True,
-                 track_stats=True, exact_steering=False, kernel="auto"):
+                 track_stats=True, exact_steering=False, kernel="auto", extended_agents=False):
         cfg = dict(manual=False, inf_obs=True, save=False, render=False, real_time=False)
         cfg.update(world_config or {})
         if cfg['manual'] or cfg['save'] or cfg['render']:
             raise NotImplementedError("manual / save / render belong to the interactive pygame front-end")
-        if not 1 <= num_agents <= _lib.MA_MAX_AGENTS:
-            # the reference raises IndexError in Scenario.observations beyond five cars
-            raise IndexError("the reference's start grid defines %d cars; num_agents=%d" % (_lib.MA_MAX_AGENTS, num_agents))
+        limit = _lib.MA_MAX_AGENTS_EXT if extended_agents else _lib.MA_MAX_AGENTS
+        if not 1 <= num_agents <= limit:
+            # the reference raises IndexError in Scenario.observations beyond five cars.  extended_agents=True
+            # opens the repo's own 6..8-car extension: an invented continuation of the start grid, specified only by the CPU
+            # restatement (oracle/ma_oracle.c) - there is no reference behaviour to be equal to.
+            raise IndexError("the reference's start grid defines %d cars; num_agents=%d%s" % (
+                _lib.MA_MAX_AGENTS, num_agents, "" if extended_agents else " (extended_agents=True allows up to %d, without reference parity)" % _lib.MA_MAX_AGENTS_EXT))
+        if num_agents > _lib.MA_MAX_AGENTS and kernel == "group":
+            raise ValueError("the 6..8-car extension is stepped by the thread-per-environment kernel only")
         if not 3 <= num_slots <= _lib.MA_MAX_SLOTS:
             raise ValueError("num_slots must be in 3..%d" % _lib.MA_MAX_SLOTS)
         self._lib = _lib.load()

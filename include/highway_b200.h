@@ -58,6 +58,9 @@ extern "C" {
 
 #define HW_SA_OBS_DIM 18
 #define HW_MA_MAX_AGENTS 5   /* the reference's start grid holds five cars (simple_base.py:32-38) */
+#define HW_MA_MAX_AGENTS_EXT 8 /* EXTENSION beyond the reference (no reference parity, the CPU restatement is its only
+                                * specification): 6..8 cars on a start grid that continues the reference's staggered rows
+                                * backwards - (2.5, lane 2), (0, lane 3), (-2.5, lane 1).  Stepped by the thread-per-environment kernel only. */
 #define HW_MA_MAX_SLOTS 16   /* live obstacles per environment (three at reset, typically <= 8) */
 #define HW_MA_OBS_DIM(A) (4 * (A) + 14)
 

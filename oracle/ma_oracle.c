@@ -32,7 +32,7 @@ enum { F_LEFT = 1, F_RIGHT = 2, F_DO_ACC = 4, F_DO_MAINT = 8 };
 enum { HW_FLAG_CONTINUOUS = 1, HW_FLAG_NO_INF_OBS = 2, HW_FLAG_NO_AUTORESET = 4, HW_FLAG_QUANTISE_F32 = 8,
        HW_FLAG_SHARED_REWARD = 16 };
 
-#define MA_MAX_A 5
+#define MA_MAX_A 8   /* 1..5: the reference's start grid; 6..8: the repo's extension (no reference behind it) */
 #define MA_MAX_K 64
 
 typedef struct { double px, py, rx, vx, vy, acc, steer, cruise; int lane, flags; } ma_car;
@@ -55,8 +55,9 @@ static inline int overlap(int ax, int ay, int bx, int by) { return ax < bx + 76 
 static void ma_reset(ma_env *e)
 {
     /* simple_base.py:32-43 "X" formation, three obstacles behind the cars */
-    static const double cx[5] = { 10.0, 10.0, 7.5, 5.0, 5.0 };
-    static const int cl[5] = { 1, 3, 2, 1, 3 };
+    /* cars 5..7 are NOT in the reference (its grid ends at five, simple_base.py:32-38): the extension continues the pattern */
+    static const double cx[8] = { 10.0, 10.0, 7.5, 5.0, 5.0, 2.5, 0.0, -2.5 };
+    static const int cl[8] = { 1, 3, 2, 1, 3, 2, 3, 1 };
     static const double ox[3] = { -20.0, -25.0, -40.0 }, ov[3] = { 7.0, 5.0, 6.0 };
     for (int i = 0; i < e->A; ++i) {
         ma_car *c = &e->car[i];

@@ -222,3 +222,36 @@ def test_full_size_properties_262144_envs():
     assert bool(torch.isfinite(ob).all()) and int(big.diagnostics().max()) == 0
     st = big.episode_statistics()
     assert st["episodes"] > n // 2
+
+
+@pytest.mark.parametrize("A,continuous", [(6, False), (8, False), (8, True), (7, True)])
+def test_extension_beyond_five_cars_matches_its_cpu_specification(A, continuous):
+    """EXTENSION, NO REFERENCE PARITY: the reference's start grid ends at five cars (simple_base.py:32-38).
+    `extended_agents=True` continues the grid to eight; the only specification of that world is the CPU restatement
+    (oracle/ma_oracle.c runs the same per-car / per-obstacle rules over more cars), which the kernel must follow bit for bit."""
+    n, steps, seed = 777, 200, 19
+    with pytest.raises(IndexError):
+        _env(4, A)
+    env = _env(n, A, continuous=continuous, seed=seed, env_id0=3, exact_steering=True, extended_agents=True)
+    assert env.obs_dim == 4 * A + 14
+    st = mo.MaState(n, A)
+    ob0 = mo.ma_reset(st)
+    assert bits_equal(env.reset().cpu().numpy(), ob0)
+    rng = np.random.RandomState(4)
+    nd = 0
+    for t in range(steps):
+        if continuous:
+            act = rng.uniform(-1, 1, (n, A, 2)).astype(np.float32); act[:, :, 1] *= 0.1
+        else:
+            act = np.where(rng.rand(n, A) < 0.7, 2, rng.randint(0, 4, (n, A))).astype(np.int32)
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        want = mo.ma_step(st, act, continuous=continuous, seed=seed, env_id0=3, quantise=True, nthreads=8)
+        d = done.cpu().numpy()
+        assert np.array_equal(d, want["done"]), "done differs at step %d" % t
+        assert bits_equal(obs.cpu().numpy(), want["obs"]), "obs differs at step %d" % t
+        assert bits_equal(rew.cpu().numpy(), f32(want["rew"])), "reward differs at step %d" % t
+        nd += int(d.any(axis=1).sum())
+    got = _read_state(env)
+    for f in MA_STATE_FIELDS + ("ep_len", "ep_ret"):
+        assert np.array_equal(getattr(got, f), getattr(st, f)), f
+    assert nd > n // 4 and int(env.diagnostics().max()) == 0

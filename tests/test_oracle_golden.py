@@ -149,3 +149,22 @@ def test_sa_oracle_matches_reference_on_unreachable_states():
     assert bits_equal(o["next_car"], g["out_car"]) and bits_equal(o["obs"], g["out_obs"]) and np.array_equal(o["next_lft"], g["out_lft"])
     y = g["out_car"][:, 1]
     assert (y == 0.0).any() and (y == 7.0).any()
+
+
+def test_ma_extension_start_grid_is_collision_free():
+    """the invented continuation of the start grid for 6..8 cars (no reference behind it): distinct, non-overlapping rects,
+    observation of length 4A + 14, and the world runs"""
+    from oracle import ma_oracle as mo
+    for A in (6, 7, 8):
+        st = mo.MaState(64, A)
+        obs = mo.ma_reset(st)
+        assert obs.shape == (64, A, 4 * A + 14) and np.isfinite(obs).all()
+        xy = {(float(st.car[0, a, 0]), int(st.lane[0, a])) for a in range(A)}
+        assert len(xy) == A
+        rng = np.random.RandomState(A)
+        ends = 0
+        for t in range(60):
+            o = mo.ma_step(st, rng.randint(0, 4, (64, A)), seed=2, quantise=True)
+            ends += int(o["done"].any(axis=1).sum())
+            assert t > 0 or not o["done"].any()      # nobody collides on the first step from the start grid
+        assert ends > 0 and st.overflow.max() == 0
