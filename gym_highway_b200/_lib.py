@@ -149,3 +149,23 @@ def sim_params(real_time=False):
         run_time += dt
         t += 1
     return HwSimParams(dt, int(ticks / 4), t)
+
+
+class _NoRange(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_RANGE = _NoRange()
+
+
+def nvtx_range(name):
+    """`with nvtx_range("hw_sa_step"):` - an NVTX range around a launch when HW_NVTX=1 (timeline tools: nsys, ncu --nvtx), a no-op
+    otherwise (the default: a range costs a microsecond of host time per call)"""
+    if os.environ.get("HW_NVTX", "0") != "1":
+        return _NO_RANGE
+    import torch
+    return torch.cuda.nvtx.range(name)

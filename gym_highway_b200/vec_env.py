@@ -237,7 +237,7 @@ class HighwayVecEnv(VecEnv):
         self._pending = None
         self._serial += 1
         out = self._out[self._cur]
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_reset"):
             rc = self._lib.hw_sa_reset(C.byref(self._state_c), None, _as_ptr(out['obs']), self.num_envs, self._stream())
         _lib.check(rc, "hw_sa_reset")
         return self._wrap(out['obs'])
@@ -246,7 +246,7 @@ class HighwayVecEnv(VecEnv):
         """reset the environments whose mask entry is non-zero (only needed with auto_reset=False)"""
         mask = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
         assert mask.numel() == self.num_envs
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_reset"):
             rc = self._lib.hw_sa_reset(C.byref(self._state_c), _as_ptr(mask), None, self.num_envs, self._stream())
         _lib.check(rc, "hw_sa_reset")
         return self.observe()
@@ -266,7 +266,7 @@ class HighwayVecEnv(VecEnv):
         a = self._coerce_actions(actions)
         self._cur ^= 1
         self._serial += 1
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_step"):
             rc = self._lib.hw_sa_step(C.byref(self._state_c), _as_ptr(a), C.byref(self._out_c[self._cur]),
                                       C.byref(self.params), self._seed, self._env_id0, self.num_envs, self._flags,
                                       self._stream())
@@ -291,7 +291,7 @@ class HighwayVecEnv(VecEnv):
         self._serial += 1
         out = _lib.HwSaOut(obs.data_ptr(), rew.data_ptr(), done.data_ptr(), self._out[0]['term'].data_ptr(),
                            self.stats.data_ptr() if self.stats is not None else 0)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_step"):
             rc = self._lib.hw_sa_step(C.byref(self._state_c), _as_ptr(actions), C.byref(out), C.byref(self.params),
                                       self._seed, self._env_id0, self.num_envs, self._flags, self._stream())
         _lib.check(rc, "hw_sa_step")
@@ -301,7 +301,7 @@ class HighwayVecEnv(VecEnv):
         returns the last step's (obs, rew, done)"""
         self._cur ^= 1
         self._serial += 1
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_rollout_random"):
             rc = self._lib.hw_sa_rollout_random(C.byref(self._state_c), C.byref(self._out_c[self._cur]),
                                                 C.byref(self.params), self._seed, self._env_id0, int(action_ctr0),
                                                 int(steps), self.num_envs, self._flags, self._stream())
@@ -327,7 +327,7 @@ class HighwayVecEnv(VecEnv):
         h['act'].copy_(torch.as_tensor(np.asarray(actions)).reshape(h['act'].shape))
         self._cur ^= 1
         self._serial += 1
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_step_host"):
             rc = self._lib.hw_sa_step_host(C.byref(self._state_c), _as_ptr(h['act']), _as_ptr(h['d_act']),
                                            C.byref(self._out_c[self._cur]), _as_ptr(h['obs']), _as_ptr(h['rew']),
                                            _as_ptr(h['done']), C.byref(self.params), self._seed, self._env_id0,

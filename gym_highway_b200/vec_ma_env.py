@@ -127,7 +127,7 @@ class HighwayMAVecEnv(VecEnv):
         self._pending = None
         self._serial += 1
         out = self._out[self._cur]
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx_range("hw_ma_reset"):
             rc = self._lib.hw_ma_reset(C.byref(self._state_c), None, _as_ptr(out['obs']), self.num_envs, self._stream())
         _lib.check(rc, "hw_ma_reset")
         return self._wrap(out['obs'])
@@ -146,7 +146,7 @@ class HighwayMAVecEnv(VecEnv):
         a = self._coerce_actions(actions)
         self._cur ^= 1
         self._serial += 1
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx_range("hw_ma_step"):
             rc = self._lib.hw_ma_step(C.byref(self._state_c), _as_ptr(a), C.byref(self._out_c[self._cur]),
                                       C.byref(self.params), self._seed, self._env_id0, self.num_envs, self._flags,
                                       self._stream())
@@ -171,7 +171,7 @@ class HighwayMAVecEnv(VecEnv):
         self._serial += 1
         out = _lib.HwMaOut(obs.data_ptr(), rew.data_ptr(), done.data_ptr(), self._out[0]['term'].data_ptr(),
                            self.stats.data_ptr() if self.stats is not None else 0)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx_range("hw_ma_step"):
             rc = self._lib.hw_ma_step(C.byref(self._state_c), _as_ptr(actions), C.byref(out), C.byref(self.params),
                                       self._seed, self._env_id0, self.num_envs, self._flags, self._stream())
         _lib.check(rc, "hw_ma_step")
@@ -189,7 +189,7 @@ class HighwayMAVecEnv(VecEnv):
         h['act'].copy_(torch.as_tensor(np.asarray(actions)).reshape(h['act'].shape))
         self._cur ^= 1
         self._serial += 1
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _lib.nvtx_range("hw_ma_step_host"):
             rc = self._lib.hw_ma_step_host(C.byref(self._state_c), _as_ptr(h['act']), _as_ptr(h['d_act']),
                                            C.byref(self._out_c[self._cur]), _as_ptr(h['obs']), _as_ptr(h['rew']),
                                            _as_ptr(h['done']), C.byref(self.params), self._seed, self._env_id0,
