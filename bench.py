@@ -344,10 +344,11 @@ def consumers_measure(dev, rank):
     rms = RunningMeanStd(shape=(A, env.obs_dim), device=dev)
     actor = torch.nn.Sequential(torch.nn.Linear(env.obs_dim, 64), torch.nn.ReLU(), torch.nn.Linear(64, 2), torch.nn.Tanh()).to(dev)
     col = MADeviceCollector(env, lambda obs: actor(obs.reshape(-1, env.obs_dim)), mem, obs_rms=rms)
-    t = timed(lambda: col.collect(T), 3)
+    t_eager = timed(lambda: col.collect(T), 3)
+    t = timed(lambda: col.collect_graphed(T), 5)
     out["maddpg_collection"] = {"workload": "MADDPG rollout loop: %d multi-agent envs x %d cars (continuous), torch actor 34-64-2, env step_into, "
-                                            "hw_ring_store into a %d-row ring, hw_obs_moments; eager launches" % (n, A, mem.limit),
-                                "transitions_per_s": n * T / t, "agent_transitions_per_s": n * A * T / t, "us_per_step": 1e6 * t / T,
+                                            "hw_ring_store into a %d-row ring, hw_obs_moments; the %d-step loop replayed from one CUDA graph" % (n, A, mem.limit, T),
+                                "transitions_per_s": n * T / t, "agent_transitions_per_s": n * A * T / t, "us_per_step": 1e6 * t / T, "us_per_step_eager": 1e6 * t_eager / T,
                                 "ring_wrapped": mem.nb_entries == mem.limit}
     del col, mem, env, rms
     torch.cuda.empty_cache()

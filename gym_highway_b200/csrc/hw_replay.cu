@@ -117,7 +117,7 @@ __global__ void ring_advance_kernel(long long *state, const long long n, const l
 // float64 column sums and sums of squares of a float32 [n][C] block, in two deterministic stages: stage 1 sums slabs of
 // kMomentRows rows per block (thread c walks its column down the slab: coalesced across the threads of a block), stage 2 adds the
 // slab results in slab order and appends the row count - the `addvec` RunningMeanStd.update builds before its Allreduce.
-constexpr int kMomentRows = 128;
+constexpr int kMomentRows = 64;
 
 __global__ void __launch_bounds__(256)
 moments_slab_kernel(const float *__restrict__ x, const long long n, const int C, double *__restrict__ partial /* [slabs][2][C] */)
@@ -126,13 +126,19 @@ moments_slab_kernel(const float *__restrict__ x, const long long n, const int C,
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= C) return;
     const long long r0 = slab * kMomentRows, r1 = r0 + kMomentRows < n ? r0 + kMomentRows : n;
-    double s = 0.0, q = 0.0;
-    for (long long r = r0; r < r1; ++r) {
-        const double v = (double)x[r * C + c];
-        s += v; q += v * v;
+    // four interleaved accumulators (rows r0 + 4j + i) so that four loads are in flight per thread; combined in a fixed order
+    double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
+    long long r = r0;
+    for (; r + 4 <= r1; r += 4) {
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = x[(r + i) * C + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const double d = (double)v[i]; s[i] += d; q[i] += d * d; }
     }
-    partial[(slab * 2 + 0) * C + c] = s;
-    partial[(slab * 2 + 1) * C + c] = q;
+    for (int i = 0; r < r1; ++r, ++i) { const double d = (double)x[r * C + c]; s[i] += d; q[i] += d * d; }
+    partial[(slab * 2 + 0) * C + c] = (s[0] + s[1]) + (s[2] + s[3]);
+    partial[(slab * 2 + 1) * C + c] = (q[0] + q[1]) + (q[2] + q[3]);
 }
 
 __global__ void __launch_bounds__(256)

@@ -220,6 +220,29 @@ class MADeviceCollector(object):
         for _ in range(nb_rollout_steps):
             self.step()
 
+    @torch.no_grad()
+    def collect_graphed(self, nb_rollout_steps):
+        """`collect(nb_rollout_steps)` replayed from ONE CUDA graph (captured on the first call after an eager warm-up run): eagerly a
+        step is a dozen small launches and the host is the bound.  The ring's start / length live on the device (`RingMemory.state`),
+        so every replay appends where the last one stopped; the host mirror is advanced by the same arithmetic.  The policy must be
+        capturable (device tensors only, no host-side state that changes per step); nb_rollout_steps must be even (the two
+        observation buffers alternate, and a replay has to start on the one the capture started on)."""
+        T = int(nb_rollout_steps)
+        if T % 2:
+            raise ValueError("collect_graphed needs an even nb_rollout_steps")
+        if getattr(self, "_graph", None) is None or self._graph_T != T:
+            self.collect(T)  # warm-up: allocator pools, cuBLAS workspaces, NCCL channels
+            torch.cuda.synchronize(self.env.device)
+            mirror = (self.memory.start, self.memory.length, self.t)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.collect(T)
+            self.memory.start, self.memory.length, self.t = mirror  # the capture recorded launches, it did not run them
+            self._graph_T = T
+        self._graph.replay()
+        self.memory._advance(T * self.env.num_envs * self.world)
+        self.t += T
+
     def finished_episodes(self):
         """(episode_reward [k, A], episode_step [k], env index [k]) of the episodes that ended on the LAST step (host copy of
         those rows only) - what the reference appends to its history deques"""

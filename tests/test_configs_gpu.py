@@ -139,3 +139,48 @@ def test_configs2_16384_ma_envs_uniform_random_actions(continuous, kernel):
     if not continuous:
         assert s["timeouts"] > 0, "no multi-agent episode reached the time-out tick (2159 -> 2160)"
     assert max_live >= 5
+
+
+def test_sweep_size_4m_sa_envs_slice_against_the_oracle():
+    """configs[4]'s 4 194 304-env point in the bit-exact mode: environments [lo, lo + m) of the big batch against the oracle stepped
+    with the slice's global env ids (the full-size tests in test_sa_gpu.py compare the kernel with itself; this one closes the loop)"""
+    from gym_highway_b200 import HighwayVecEnv
+    n, lo, m, seed, steps = 4194304, 3000001, 2048, 29, 120
+    env = HighwayVecEnv(n, seed=seed, exact_steering=True)
+    st = orc.SaState(m)
+    orc.sa_reset(st)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    nd = 0
+    for t in range(steps):
+        act = torch.randint(0, 4, (n,), generator=g, device="cuda", dtype=torch.int32)
+        obs, rew, done, _ = env.step(act)
+        want = orc.sa_step(st, act[lo:lo + m].cpu().numpy(), seed=seed, env_id0=lo, quantise=True, nthreads=NTHREADS)
+        assert np.array_equal(done[lo:lo + m].cpu().numpy(), want["done"]), "done differs at step %d" % t
+        assert bits_equal(obs[lo:lo + m].cpu().numpy(), want["obs"]), "obs differs at step %d" % t
+        assert bits_equal(rew[lo:lo + m].cpu().numpy(), f32(want["rew"])), "reward differs at step %d" % t
+        nd += int(want["done"].sum())
+    assert nd > m // 20
+
+
+@pytest.mark.parametrize("continuous", [False, True])
+def test_sweep_size_262144_ma_envs_slice_against_the_oracle(continuous):
+    """the 262 144-env multi-agent sweep point (thread-per-environment kernel), bit-exact mode: a slice against the oracle"""
+    from gym_highway_b200 import HighwayMAVecEnv
+    n, A, lo, m, seed, steps = 262144, 5, 200003, 1500, 31, 100
+    env = HighwayMAVecEnv(n, num_agents=A, continuous=continuous, seed=seed, exact_steering=True)
+    st = mo.MaState(m, A)
+    mo.ma_reset(st)
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    nd = 0
+    for t in range(steps):
+        if continuous:
+            act = torch.rand((n, A, 2), generator=g, device="cuda") * 2 - 1
+        else:
+            act = torch.randint(0, 4, (n, A), generator=g, device="cuda", dtype=torch.int32)
+        obs, rew, done, _ = env.step(act)
+        want = mo.ma_step(st, act[lo:lo + m].cpu().numpy(), continuous=continuous, seed=seed, env_id0=lo, quantise=True, nthreads=NTHREADS)
+        assert np.array_equal(done[lo:lo + m].cpu().numpy(), want["done"]), "done differs at step %d" % t
+        assert bits_equal(obs[lo:lo + m].cpu().numpy(), want["obs"]), "obs differs at step %d" % t
+        assert bits_equal(rew[lo:lo + m].cpu().numpy(), f32(want["rew"])), "reward differs at step %d" % t
+        nd += int(want["done"].any(axis=1).sum())
+    assert nd > m and int(env.diagnostics().max()) == 0 and st.overflow.max() == 0

@@ -94,6 +94,35 @@ def test_device_collector_matches_reference_memory():
     assert np.allclose(st["epoch_episode_rewards"].numpy(), np.sum(np.asarray(rews, np.float64), axis=0), rtol=1e-12)
 
 
+def test_device_collector_graph_replay_equals_eager_collection():
+    """MADeviceCollector.collect_graphed: the rollout loop replayed from one CUDA graph leaves the ring, its device-side position,
+    the episode bookkeeping and obs_rms exactly where the eager loop leaves them"""
+    from gym_highway_b200 import HighwayMAVecEnv
+    from gym_highway_b200.replay import MADeviceCollector, RingMemory, RunningMeanStd
+    torch.manual_seed(0)
+    n, A, T = 3000, 5, 6
+    actor = torch.nn.Sequential(torch.nn.Linear(34, 32), torch.nn.Tanh(), torch.nn.Linear(32, 2), torch.nn.Tanh()).cuda()
+
+    def make():
+        env = HighwayMAVecEnv(n, num_agents=A, continuous=True, seed=8)
+        mem = RingMemory(n * 5 * T // 2, A, env.obs_dim, 2, device=env.device)     # wraps during the run
+        rms = RunningMeanStd(shape=(A, env.obs_dim), device=env.device)
+        return MADeviceCollector(env, lambda obs: actor(obs.reshape(-1, 34)), mem, obs_rms=rms), mem, rms
+
+    (ce, me, re_), (cg, mg, rg) = make(), make()
+    for _ in range(4):
+        ce.collect(T)
+        cg.collect_graphed(T)       # first call: eager warm-up + capture + one replay = two rollouts
+    ce.collect(T)
+    for k in ("obs0", "obs1", "actions", "rewards", "terminals1"):
+        assert torch.equal(getattr(me, k), getattr(mg, k)), k
+    assert (me.start, me.length) == (mg.start, mg.length) and mg.state.tolist() == me.state.tolist() == [mg.start, mg.length, 5 * T * n]
+    assert torch.equal(ce.ep_reward, cg.ep_reward) and torch.equal(ce.ep_step, cg.ep_step) and torch.equal(ce.epoch_counts, cg.epoch_counts)
+    assert torch.equal(re_._sum, rg._sum) and float(re_._count) == float(rg._count) and ce.t == cg.t == 5 * T
+    with pytest.raises(ValueError):
+        cg.collect_graphed(3)
+
+
 def test_gae_and_nstep_kernels_are_bit_exact_with_the_reference_precisions():
     import ctypes as C
     from gym_highway_b200 import _lib
