@@ -342,11 +342,11 @@ def consumers_measure(dev, rank):
     env = HighwayMAVecEnv(n, num_agents=A, continuous=True, seed=0, device=dev, env_id0=rank * n)
     mem = RingMemory(n * 12, A, env.obs_dim, 2, device=dev)
     rms = RunningMeanStd(shape=(A, env.obs_dim), device=dev)
-    actor = torch.nn.Sequential(torch.nn.Linear(env.obs_dim, 64), torch.nn.ReLU(), torch.nn.Linear(64, 2), torch.nn.Tanh()).to(dev)
-    col = MADeviceCollector(env, lambda obs: actor(obs.reshape(-1, env.obs_dim)), mem, obs_rms=rms)
+    actor = torch.nn.Sequential(torch.nn.Linear(env.obs_dim, 64), torch.nn.ReLU(), torch.nn.Linear(64, 2), torch.nn.Tanh()).to(dev).to(torch.bfloat16)
+    col = MADeviceCollector(env, lambda obs: actor(obs.reshape(-1, env.obs_dim).to(torch.bfloat16)), mem, obs_rms=rms)
     t_eager = timed(lambda: col.collect(T), 3)
     t = timed(lambda: col.collect_graphed(T), 5)
-    out["maddpg_collection"] = {"workload": "MADDPG rollout loop: %d multi-agent envs x %d cars (continuous), torch actor 34-64-2, env step_into, "
+    out["maddpg_collection"] = {"workload": "MADDPG rollout loop: %d multi-agent envs x %d cars (continuous), torch actor 34-64-2 (bf16), env step_into, "
                                             "hw_ring_store into a %d-row ring, hw_obs_moments; the %d-step loop replayed from one CUDA graph" % (n, A, mem.limit, T),
                                 "transitions_per_s": n * T / t, "agent_transitions_per_s": n * A * T / t, "us_per_step": 1e6 * t / T, "us_per_step_eager": 1e6 * t_eager / T,
                                 "ring_wrapped": mem.nb_entries == mem.limit}

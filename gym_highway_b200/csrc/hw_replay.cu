@@ -141,17 +141,26 @@ moments_slab_kernel(const float *__restrict__ x, const long long n, const int C,
     partial[(slab * 2 + 1) * C + c] = (q[0] + q[1]) + (q[2] + q[3]);
 }
 
-__global__ void __launch_bounds__(256)
+// stage 2: out[c] = sum over the slabs of partial[slab][c], c over the 2C {sum, sum of squares} columns.  A block owns 32 consecutive
+// columns (coalesced 256-byte rows); its 32 slab groups (threadIdx.y) each add every 32nd slab in order, and the 32 group sums are
+// then added in group order - a fixed summation tree, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(1024)
 moments_finish_kernel(const double *__restrict__ partial, const long long slabs, const int C, const double count, double *__restrict__ out /* [2C + 1] */)
 {
-    const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c < 2 * C) {
-        const int which = c / C, col = c - which * C;
-        double s = 0.0;
-        for (long long k = 0; k < slabs; ++k) s += partial[(k * 2 + which) * C + col];
-        out[c] = s;
+    __shared__ double part[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    if (c < 2 * C)
+        for (long long k = threadIdx.y; k < slabs; k += 32) s += partial[k * 2 * C + c];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < 2 * C) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < 32; ++g) t += part[g][threadIdx.x];
+        out[c] = t;
     }
-    if (c == 0) out[2 * C] = count;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) out[2 * C] = count;
 }
 
 }  // namespace hw
@@ -206,6 +215,6 @@ extern "C" int hw_obs_moments(const float *x, int64_t n, int cols, double count,
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((unsigned)((cols + 255) / 256), (unsigned)slabs);
     hw::moments_slab_kernel<<<grid, 256, 0, s>>>(x, n, cols, workspace);
-    hw::moments_finish_kernel<<<(unsigned)((2 * cols + 255) / 256), 256, 0, s>>>(workspace, slabs, cols, count, out);
+    hw::moments_finish_kernel<<<(unsigned)((2 * cols + 31) / 32), dim3(32, 32), 0, s>>>(workspace, slabs, cols, count, out);
     return (int)cudaGetLastError();
 }

@@ -1,3 +1,12 @@
-python -m pytest tests/test_configs_gpu.py tests/test_reference_gpu.py -x -q > gpurun_out/r3e_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/r3e_tests.log
-tail -6 gpurun_out/r3e_tests.log
-python bench.py > gpurun_out/r3e_bench.json 2> gpurun_out/r3e_bench.err; echo "bench rc $?"; tail -3 gpurun_out/r3e_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r3g_collector_launches.csv python scripts/perf_collector.py > /dev/null 2>&1
+python - <<'PY'
+import csv
+rows=list(csv.reader(open('gpurun_out/r3g_collector_launches.csv')))
+hdr=None; seq=[]
+for r in rows:
+    if 'Kernel Name' in r: hdr=r; continue
+    if hdr and len(r)==len(hdr):
+        d=dict(zip(hdr,r)); seq.append((d['Kernel Name'][:70], float(d['Metric Value'].replace(',',''))/1e3))
+# last step's launches
+for k,v in seq[-16:]: print('%8.1f us  %s' % (v,k))
+PY
