@@ -1,12 +1,4 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r3g_collector_launches.csv python scripts/perf_collector.py > /dev/null 2>&1
-python - <<'PY'
-import csv
-rows=list(csv.reader(open('gpurun_out/r3g_collector_launches.csv')))
-hdr=None; seq=[]
-for r in rows:
-    if 'Kernel Name' in r: hdr=r; continue
-    if hdr and len(r)==len(hdr):
-        d=dict(zip(hdr,r)); seq.append((d['Kernel Name'][:70], float(d['Metric Value'].replace(',',''))/1e3))
-# last step's launches
-for k,v in seq[-16:]: print('%8.1f us  %s' % (v,k))
-PY
+python -m pytest tests/test_ma_gpu.py tests/test_reference_gpu.py tests/test_configs_gpu.py -x -q -k "thread or golden or vecenv or ma or extension" > gpurun_out/r3j_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/r3j_tests.log
+tail -4 gpurun_out/r3j_tests.log
+python scripts/perf_ma.py 65536 131072 262144 2>&1 | tail -5
+ncu --set full --clock-control none --import-source on -k regex:ma_tpe_step_kernel -s 40 -c 1 -f -o gpurun_out/prof_ma_tpe_r3j python scripts/perf_ma.py 262144 > gpurun_out/r3j_ncu_ma.log 2>&1
