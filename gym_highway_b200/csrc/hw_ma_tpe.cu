@@ -37,6 +37,35 @@ constexpr int kTpeBlock = HW_TPE_BLOCK;
 #endif
 constexpr int kTpeWarpDoubles = HW_TPE_SLOTS * O_NF * 32;  // one warp's obstacle region: 16 KB for 16 slots
 
+// Conditional moves of doubles.  HW_TPE_FSEL = 0: the shared helpers (one predicated DMUL / predicated moves: fewest issue slots,
+// but the move sits on the fp64 pipe with its latency); 1: selp.f64, i.e. a pair of 32-bit selects on the ALU pipe (one more
+// instruction, a third of the latency) - this kernel is bound by dependent-instruction latency, not by issue slots.
+#ifndef HW_TPE_FSEL
+#define HW_TPE_FSEL 0
+#endif
+#if HW_TPE_FSEL
+__device__ __forceinline__ void tmov_if(bool p, double &x, double y)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\tselp.f64 %0, %2, %0, q;\n\t}" : "+d"(x) : "r"((int)p), "d"(y));
+}
+__device__ __forceinline__ void tmov_if_nz(uint32_t w, double &x, double y)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\tselp.f64 %0, %2, %0, q;\n\t}" : "+d"(x) : "r"(w), "d"(y));
+}
+__device__ __forceinline__ void tset_if(bool p, double &x, double c) { tmov_if(p, x, c); }
+__device__ __forceinline__ double tclamp(double x, const double lo, const double hi)
+{
+    tset_if(hi < x, x, hi);
+    tset_if(!(x > lo), x, lo);
+    return x;
+}
+#else
+__device__ __forceinline__ void tmov_if(bool p, double &x, double y) { dmov_if(p, x, y); }
+__device__ __forceinline__ void tmov_if_nz(uint32_t w, double &x, double y) { dmov_if_nz(w, x, y); }
+__device__ __forceinline__ void tset_if(bool p, double &x, double c) { dset_if(p, x, c); }
+__device__ __forceinline__ double tclamp(double x, const double lo, const double hi) { return py_clamp(x, lo, hi); }
+#endif
+
 struct TpeOb {  // this thread's column of the warp-private obstacle region
     double *base;
     __device__ __forceinline__ double &operator()(int k, int f) const { return base[(k * O_NF + f) * 32]; }
@@ -192,8 +221,8 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
 #pragma unroll
     for (int a = 0; a < A; ++a) {
         if (CONT) {
-            c.acc[a] = py_clamp(dadd(c.acc[a], a0[a]), -5.0, 5.0);
-            c.steer[a] = py_clamp(dadd(c.steer[a], a1[a]), -30.0, 30.0);
+            c.acc[a] = tclamp(dadd(c.acc[a], a0[a]), -5.0, 5.0);
+            c.steer[a] = tclamp(dadd(c.steer[a], a1[a]), -30.0, 30.0);
             continue;
         }
         // amask = the mode bit the action asks for; it fires when not yet set.  The two modes of a pair exclude each other, so
@@ -211,7 +240,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
             for (int j = 0; j < A; ++j) {
                 if (j == a) continue;
                 const bool take = (c.ln[j] == lane) & (c.px[j] > c.px[a]) & (c.px[j] < bpx);
-                dmov_if(take, bpx, c.px[j]); dmov_if(take, bvx, c.vx[j]);
+                tmov_if(take, bpx, c.px[j]); tmov_if(take, bvx, c.vx[j]);
             }
             const uint32_t diff = h.olane ^ ((uint32_t)lane * 0x55555555u);
             uint32_t same = ~(diff | (diff >> 1)) & 0x55555555u & live;
@@ -220,14 +249,14 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
                 same &= same - 1u;
                 const double opx = ob(k, O_PX), ovx = ob(k, O_VX);
                 const bool take = (opx > c.px[a]) & (opx < bpx);
-                dmov_if(take, bpx, opx); dmov_if(take, bvx, ovx);
+                tmov_if(take, bpx, opx); tmov_if(take, bvx, ovx);
             }
             c.cruise[a] = bvx;
         }
         const int dl = (int)((fire >> 19) & 1u) - (int)((fire >> 18) & 1u);  // RIGHT +1, LEFT -1, only when it fires
         c.ln[a] = min(max(c.ln[a] + dl, 1), 3);
-        c.acc[a] = py_clamp(c.acc[a], -5.0, 5.0);
-        c.steer[a] = py_clamp(c.steer[a], -30.0, 30.0);
+        c.acc[a] = tclamp(c.acc[a], -5.0, 5.0);
+        c.steer[a] = tclamp(c.steer[a], -30.0, 30.0);
     }
 
     // ---- car updates in id order against last tick's leader (agent.py:79-165): a car subtracts the leader's velocity "as it is
@@ -237,60 +266,60 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
     const int L = (int)h.leader;
     double lv_old = c.vx[0];
 #pragma unroll
-    for (int j = 1; j < A; ++j) dmov_if(L == j, lv_old, c.vx[j]);
+    for (int j = 1; j < A; ++j) tmov_if(L == j, lv_old, c.vx[j]);
 #pragma unroll
     for (int a = 0; a < A; ++a) {
         uint32_t b = c.b[a];
         if (!CONT) {
             const bool m_acc = (b & kBitDoAcc) != 0, m_maint = (b & kBitDoMaint) != 0;  // never both
             double acc_a = dadd(c.acc[a], dt);
-            dset_if(c.acc[a] < 0.0, acc_a, 0.0);
+            tset_if(c.acc[a] < 0.0, acc_a, 0.0);
             const double vc = ceil(c.vx[a]), cc = ceil(c.cruise[a]);
             const bool snap = m_maint && vc == cc;
             const double acc_m = __hiloint2double(snap ? 0 : ((vc <= cc) ? 0x40140000 : (int)0xC0140000), 0);  // 0.0, 5.0, -5.0
-            dmov_if_nz(b & kBitDoAcc, c.acc[a], acc_a);
-            dmov_if_nz(b & kBitDoMaint, c.acc[a], acc_m);
-            dmov_if(snap, c.vx[a], c.cruise[a]);
+            tmov_if_nz(b & kBitDoAcc, c.acc[a], acc_a);
+            tmov_if_nz(b & kBitDoMaint, c.acc[a], acc_m);
+            tmov_if(snap, c.vx[a], c.cruise[a]);
             if (m_acc && c.acc[a] == 5.0) b &= ~kBitDoAcc;
             if (snap) b &= ~kBitDoMaint;
         }
-        c.vx[a] = py_clamp(dadd(c.vx[a], dmul(c.acc[a], dt)), 0.0, 20.0);
+        c.vx[a] = tclamp(dadd(c.vx[a], dmul(c.acc[a], dt)), 0.0, 20.0);
         if (!CONT) {
             const double ty = __fma_rn((double)c.ln[a], 2.5, -1.25);  // lane 1, 2, 3: 1.25, 3.75, 6.25 (exact)
             const bool m_left = (b & kBitLeft) != 0, m_right = (b & kBitRight) != 0;  // never both
             double inc = 0.0;
-            dmov_if(m_left, inc, C.k30dt); dmov_if(m_right, inc, -C.k30dt);
+            tmov_if(m_left, inc, C.k30dt); tmov_if(m_right, inc, -C.k30dt);
             c.steer[a] = dadd(c.steer[a], inc);  // + 0.0 is the identity on every value steer can hold
             const bool reached = (m_left && c.py[a] <= ty) || (m_right && c.py[a] >= ty);
-            dset_if(reached, c.steer[a], 0.0);
+            tset_if(reached, c.steer[a], 0.0);
             if (reached) b &= ~(kBitLeft | kBitRight);
         }
         c.b[a] = b;
     }
     double lv = c.vx[0];  // the leader's velocity "as it is now" for the cars after it: its new value
 #pragma unroll
-    for (int j = 1; j < A; ++j) dmov_if(L == j, lv, c.vx[j]);
+    for (int j = 1; j < A; ++j) tmov_if(L == j, lv, c.vx[j]);
     double ang[A];
 #pragma unroll
     for (int a = 0; a < A; ++a) {
         // evaluated unconditionally (tan(0) = 0 gives 0 as well; a division by 4 / tan(0) = inf gives 0): no branch between the cars
         ang[a] = angular_velocity<EXACT>(c.vx[a], c.steer[a]);
-        dset_if(!(c.steer[a] != 0.0), ang[a], 0.0);
+        tset_if(!(c.steer[a] != 0.0), ang[a], 0.0);
         if (!CONT) c.vy[a] = ang[a];  // agent.py:144: velocity.y = angular_velocity (discrete update only)
     }
 #pragma unroll
     for (int a = 0; a < A; ++a) {
         double lva = lv_old;
-        dmov_if(L < a, lva, lv);
+        tmov_if(L < a, lva, lv);
         const double vdt = dmul(c.vx[a], dt);
         double px = dadd(c.px[a], vdt);
         double py = dadd(c.py[a], dmul(c.vy[a], dt));
         if (CONT) py = dsub(py, dmul(ang[a], dt));
         else      py = dsub(py, dmul(dmul(dmul(ang[a], kRad2Deg), dt), dt));
         px = dsub(px, dmul(lva, dt));
-        dset_if(L == a, px, 10.0);
-        dset_if(7.0 < py, py, 7.0);   // if y < 1: y = 1 elif y > 6: y = min(y, 7)
-        dset_if(py < 1.0, py, 1.0);
+        tset_if(L == a, px, 10.0);
+        tset_if(7.0 < py, py, 7.0);   // if y < 1: y = 1 elif y > 6: y = min(y, 7)
+        tset_if(py < 1.0, py, 1.0);
         c.rx[a] = dadd(c.rx[a], vdt);
         c.px[a] = px; c.py[a] = py;
         if (CONT) {
@@ -307,8 +336,8 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
 #pragma unroll
     for (int j = 1; j < A; ++j) {
         const bool up = c.px[j] > plead, dn = c.px[j] <= plast;  // first of the maxima, last of the minima
-        lead = up ? j : lead; dmov_if(up, plead, c.px[j]); dmov_if(up, lead_rx, c.rx[j]);
-        dmov_if(dn, plast, c.px[j]); dmov_if(dn, last_rx, c.rx[j]);
+        lead = up ? j : lead; tmov_if(up, plead, c.px[j]); tmov_if(up, lead_rx, c.rx[j]);
+        tmov_if(dn, plast, c.px[j]); tmov_if(dn, last_rx, c.rx[j]);
     }
     h.leader = (uint32_t)lead;
 
@@ -333,11 +362,11 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         for (int j = 0; j < A; ++j) {
             const double d = dsub(c.rx[j], orx);
             const bool take = (c.ln[j] == lane) & (orx < c.rx[j]) & (d < bd);  // first wins ties
-            dmov_if(take, bd, d); dmov_if(take, bv, c.vx[j]);
+            tmov_if(take, bd, d); tmov_if(take, bv, c.vx[j]);
         }
-        double v = py_clamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
-        dmov_if(bd < tpe_inf(), v, iv);        // else min(init_vx, that car's vx)
-        dmov_if(bv < iv, v, bv);
+        double v = tclamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
+        tmov_if(bd < tpe_inf(), v, iv);        // else min(init_vx, that car's vx)
+        tmov_if(bv < iv, v, bv);
         const double odt = dmul(v, dt);
         const double opx = dsub(dadd(ob(k, O_PX), odt), lvdt);
         const double orx2 = dadd(orx, odt);
@@ -396,7 +425,7 @@ __device__ __forceinline__ uint32_t tpe_observe_obstacles(MaHead &h, const TpeCa
             for (int a = 0; a < A; ++a) {
                 const double d = fabs(dsub(c.rx[a], krx));
                 const bool take = d < nd[a];
-                dmov_if(take, nd[a], d); dmov_if(take, brx[a], krx); dmov_if(take, bvx[a], kvx);
+                tmov_if(take, nd[a], d); tmov_if(take, brx[a], krx); tmov_if(take, bvx[a], kvx);
             }
         }
         if (none) { h.flags |= 2u; nolane |= 1u << l; }
@@ -524,7 +553,7 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
 #pragma unroll
         for (int a = 0; a < A; ++a) {
             r[a] = dsub(ddiv_const(c.vx[a], 20.0), 1.0);
-            dset_if(((hit >> a) & 1u) != 0u, r[a], -250.0);
+            tset_if(((hit >> a) & 1u) != 0u, r[a], -250.0);
             rsum = dadd(rsum, r[a]);
         }
 #pragma unroll

@@ -36,6 +36,25 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert b"aligned" in lib.hw_error_string(-2)
 
 
+def test_consumer_entry_points_reject_bad_arguments_without_a_gpu():
+    from gym_highway_b200 import _lib
+    lib = _lib.load()
+    ring = _lib.HwRing(0, 0, 0, 0, 0, 0)
+    blk = _lib.HwTransitionBlock(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    assert lib.hw_ring_store(ctypes.byref(ring), ctypes.byref(blk), None, 8, 5, 34, 2, 100, 1.0, None) == -1   # null ring arrays
+    assert lib.hw_ring_store(None, ctypes.byref(blk), None, 8, 5, 34, 2, 100, 1.0, None) == -1
+    ring = _lib.HwRing(16, 16, 16, 16, 16, 16)
+    assert lib.hw_ring_store(ctypes.byref(ring), ctypes.byref(blk), None, 8, 5, 34, 2, 100, 1.0, None) == -1   # null block arrays
+    assert lib.hw_ring_store(ctypes.byref(ring), ctypes.byref(blk), None, 0, 5, 34, 2, 100, 1.0, None) == -1   # no transitions
+    assert lib.hw_obs_moments(None, 8, 170, 8.0, None, None, None) == -1
+    # workspace of the two-stage column sums: one {sum, sum of squares} row of doubles per 64-row slab
+    assert lib.hw_obs_moments_workspace(1000, 170) == 16 * 2 * 170 * 8 and lib.hw_obs_moments_workspace(0, 170) == 0
+    assert lib.hw_gae(None, None, None, None, 0.99, 0.95, None, None, 5, 8, None) == -1
+    assert lib.hw_nstep_returns(None, None, None, 0.99, None, 5, 8, None) == -1
+    st = _lib.HwMaState(16, 16, 16, 9, 16)                                     # more cars than the extension's eight
+    assert lib.hw_ma_reset(ctypes.byref(st), None, None, 4, None) == -1
+
+
 def test_sim_params_follow_the_reference_clock():
     from gym_highway_b200 import _lib
     p = _lib.sim_params(False)
