@@ -115,11 +115,12 @@ def workload_info(args):
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_arm(args, info, steps_hint=0, nthreads=None, warmup=3):
-    """time the C restatement of the reference step on the host cores: bounded sample of the workload"""
+def cpu_arm(args, info, steps_hint=0, nthreads=None, warmup=3, full_batch=False):
+    """time the C restatement of the reference step on the host cores: a bounded sample of the workload (65,536 envs per step for
+    the cpu_baseline leg of the GPU arm; the workload's own batch for `--impl reference`, where a step of 4,194,304 envs is ~0.25 s)"""
     from oracle import oracle as orc
     nthreads = nthreads or os.cpu_count() or 1
-    n = min(args.envs, 65536)
+    n = args.envs if full_batch else min(args.envs, 65536)
     rng = np.random.RandomState(1234)
     if info["kind"] == "sa":
         st = orc.SaState(n)
@@ -158,12 +159,13 @@ def reference_main(args, info):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # each "step" of this arm is one env.step of a bounded 65,536-env sample of the workload on all host cores
-    base = cpu_arm(args, info, steps_hint=args.cpu_steps or args.steps, warmup=args.warmup)
+    # each "step" of this arm is one env.step of the arm's own batch (the same envs per GPU as the GPU arm) on all host cores; the
+    # number of steps is the requested one, capped so that the run stays within a minute
+    base = cpu_arm(args, info, steps_hint=args.cpu_steps or args.steps, warmup=args.warmup, full_batch=True)
     line = {"impl": "reference", "metric": "env-steps/s", "value": base["value"], "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": base["steps"], "warmup": max(3, args.warmup), "ms_per_step": base["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": info["name"], "envs_per_step_sample": base["envs"], "requested_steps": args.steps},
+            "config": {"workload": info["name"], "envs_per_gpu": args.envs, "envs_per_step_sample": base["envs"], "requested_steps": args.steps},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
