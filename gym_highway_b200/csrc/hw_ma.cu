@@ -189,7 +189,7 @@ static int ma_launch_step(const HwMaState *st, const void *actions, const HwMaOu
     C_.dt = P->dt; C_.k30dt = 30.0 * P->dt; C_.ticks_per_step = P->ticks_per_step; C_.timeout_tick = P->timeout_tick;
     // two layouts of the same step (identical results): a thread per environment with the cars in registers (hw_ma_tpe.cu: fewest
     // instructions per environment, 283 us against 371 us at 262 144 environments) or a lane per car (hw_ma_grp.cu: five times the
-    // threads, the better fit for a batch too small to fill the GPU - 41 us against 53 us at 16 384)
+    // threads, the better fit for the smallest batches - 41 us against 51 us at 16 384; the crossover is at ~24 576)
     if (st->num_agents > kMaxA && (flags & HW_FLAG_MA_LANE_PER_CAR)) return HW_E_BADARG;  // the extension (6..8 cars) has one kernel
     const bool tpe = (flags & HW_FLAG_MA_THREAD_PER_ENV) || st->num_agents > kMaxA
                      || (!(flags & HW_FLAG_MA_LANE_PER_CAR) && n >= HW_MA_TPE_MIN_ENVS);

@@ -48,7 +48,7 @@ extern "C" {
                                        * size - the thread-per-environment kernel from HW_MA_TPE_MIN_ENVS environments up (fewer
                                        * instructions per environment), the lane-per-car kernel below (five times the threads for a
                                        * batch that cannot fill the GPU otherwise).  Same results either way. */
-#define HW_MA_TPE_MIN_ENVS 65536
+#define HW_MA_TPE_MIN_ENVS 24576
 
 /* discrete actions, gym_highway/envs/highway_env.py:14-20 */
 #define HW_ACT_LEFT 0
