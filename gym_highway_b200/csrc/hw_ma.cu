@@ -191,8 +191,12 @@ static int ma_launch_step(const HwMaState *st, const void *actions, const HwMaOu
     // instructions per environment, 283 us against 371 us at 262 144 environments) or a lane per car (hw_ma_grp.cu: five times the
     // threads, the better fit for the smallest batches - 41 us against 51 us at 16 384; the crossover is at ~24 576)
     if (st->num_agents > kMaxA && (flags & HW_FLAG_MA_LANE_PER_CAR)) return HW_E_BADARG;  // the extension (6..8 cars) has one kernel
+    // measured crossover (B200): the lane-per-car kernel always spends five lanes per environment, so the fewer the cars the
+    // earlier the thread-per-environment kernel wins - at every size for one or two cars, from 8 192 / 16 384 / 24 576
+    // environments for three / four / five
+    const int64_t tpe_min = (st->num_agents <= 2) ? 0 : (int64_t)(HW_MA_TPE_MIN_ENVS / 3) * (st->num_agents - 2);
     const bool tpe = (flags & HW_FLAG_MA_THREAD_PER_ENV) || st->num_agents > kMaxA
-                     || (!(flags & HW_FLAG_MA_LANE_PER_CAR) && n >= HW_MA_TPE_MIN_ENVS);
+                     || (!(flags & HW_FLAG_MA_LANE_PER_CAR) && n >= tpe_min);
     if (tpe) return ma_tpe_launch_step(st, actions, out, C_, seed, env_id0, n, flags, stream);
     return ma_grp_launch_step(st, actions, out, C_, seed, env_id0, n, flags, stream);
 }

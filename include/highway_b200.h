@@ -45,9 +45,10 @@ extern "C" {
                                     * (slower; floats then match the fp64 reference bit for bit after fp32 rounding) */
 #define HW_FLAG_MA_THREAD_PER_ENV 64  /* multi-agent step: force the one-thread-per-environment kernel (cars in registers, hw_ma_tpe.cu) */
 #define HW_FLAG_MA_LANE_PER_CAR  128  /* multi-agent step: force the lane-per-car kernel (hw_ma_grp.cu).  Neither flag: chosen by batch
-                                       * size - the thread-per-environment kernel from HW_MA_TPE_MIN_ENVS environments up (fewer
-                                       * instructions per environment), the lane-per-car kernel below (five times the threads for a
-                                       * batch that cannot fill the GPU otherwise).  Same results either way. */
+                                       * size - the thread-per-environment kernel from HW_MA_TPE_MIN_ENVS environments up for five cars
+                                       * (a third / two thirds of that for three / four cars, always for one or two: fewer instructions
+                                       * per environment), the lane-per-car kernel below (five times the threads for the smallest
+                                       * batches).  Same results either way. */
 #define HW_MA_TPE_MIN_ENVS 24576
 
 /* discrete actions, gym_highway/envs/highway_env.py:14-20 */
