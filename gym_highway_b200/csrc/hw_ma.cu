@@ -1,4 +1,6 @@
-// Multi-agent highway step path for sm_100a: one thread per environment (A <= 5 cars, K <= 16 obstacle slots).
+// Multi-agent highway path for sm_100a: C-ABI entry points, argument checks, kernel selection, and the reset / observe kernels
+// (A <= 5 cars - 8 with the extension -, K <= 16 obstacle slots).  The step kernels themselves are hw_ma_tpe.cu (a thread per
+// environment, cars in registers) and hw_ma_grp.cu (a lane per car).
 //
 // Replaces, for a whole batch per launch, the reference's
 //   MultiAgentEnv.step / MultiAgentEnvContinuous.step  gym_highway/multiagent_envs/highway_env.py:63-99, highway_ma_c_env.py:56-82
@@ -9,11 +11,8 @@
 //   Scenario.observations + _get_obs_norm              simple_base.py:82-154, highway_env.py:139-149
 //   reset + DummyVecMAEnv auto-reset + Monitor         highway_core.py:190-243, dummy_vec_ma_env.py:66-79, bench/monitor.py:58-79
 //
-// The simulator is order dependent (cars act and move in id order and see each other's partially updated
-// state; obstacles are an insertion-ordered list that grows and shrinks), which one thread per environment
-// reproduces by construction.  The fp32 state is promoted to fp64 in SHARED memory for the duration of the
-// step ([field][thread] layout: every access is conflict free), the ticks run op-for-op like the reference,
-// and the state is rounded back to fp32 once at the end.
+// The reset / observe kernels below run one thread per environment with the fp32 state promoted to fp64 in shared memory
+// ([field][thread] layout: every access is conflict free); they are not on the per-step path.
 #include "hw_ma_common.cuh"
 
 namespace hw {

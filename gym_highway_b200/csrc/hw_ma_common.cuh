@@ -1,4 +1,4 @@
-// Declarations shared by the two multi-agent step kernels (thread per environment: hw_ma.cu, eight lanes per
+// Declarations shared by the multi-agent kernels (entry points, reset / observe: hw_ma.cu; thread per environment: hw_ma_tpe.cu; lanes per
 // environment: hw_ma_grp.cu).
 #pragma once
 #include "hw_common.cuh"

@@ -1,10 +1,10 @@
 // Multi-agent highway step for sm_100a, G lanes per environment (G = 5: six environments per warp, two idle lanes).
 //
-// Same path as hw_ma.cu (thread per environment): MultiAgentEnv.step, highway_core.HighwaySimulator.act,
+// Same path as hw_ma_tpe.cu (thread per environment; entry points in hw_ma.cu): MultiAgentEnv.step, highway_core.HighwaySimulator.act,
 // agent.Car.update_d/update_c, agent.Obstacle.update, check_collisions, Scenario.rewards/observations, the
 // auto-reset of DummyVecMAEnv and Monitor's episode record (file:line citations at each stage below).
 //
-// Why a second layout.  With one thread per environment the fp64 working set of an environment (5 cars x 8 fields +
+// Why this layout (it was the second one, after a thread per environment with ALL state in shared memory).  With one thread per environment and the fp64 working set of an environment (5 cars x 8 fields +
 // 16 obstacle slots x 4 fields = 832 B) has to sit in shared memory, which caps an SM at 8 warps; the kernel
 // is bound by the latency of one thread walking cars and obstacles one after the other (issue slots 28 % busy).
 // Here lane g of an environment's group IS car g (its state stays in registers for the whole step) and owns the
