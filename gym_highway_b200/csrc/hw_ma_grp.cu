@@ -4,9 +4,9 @@
 // agent.Car.update_d/update_c, agent.Obstacle.update, check_collisions, Scenario.rewards/observations, the
 // auto-reset of DummyVecMAEnv and Monitor's episode record (file:line citations at each stage below).
 //
-// Why this layout (it was the second one, after a thread per environment with ALL state in shared memory).  With one thread per environment and the fp64 working set of an environment (5 cars x 8 fields +
-// 16 obstacle slots x 4 fields = 832 B) has to sit in shared memory, which caps an SM at 8 warps; the kernel
-// is bound by the latency of one thread walking cars and obstacles one after the other (issue slots 28 % busy).
+// Why this layout (historically the second one).  The first kernel ran a thread per environment with ALL of the environment's fp64
+// working set (5 cars x 8 fields + 16 obstacle slots x 4 fields = 832 B) in shared memory, which capped an SM at 8 warps and left it
+// bound by the latency of one thread walking cars and obstacles one after the other (issue slots 28 % busy).
 // Here lane g of an environment's group IS car g (its state stays in registers for the whole step) and owns the
 // obstacle slots g, g + G, ...; what the other lanes need of a car (position, velocity, lane, rect) is published
 // in shared memory, and the stages of a tick are separated by full-mask __syncwarp (control flow is uniform over the
