@@ -35,16 +35,42 @@ def needs_build():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """compile every CUDA source into one shared library; returns its path"""
-    if not force and not needs_build():
-        return LIB
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    extra = os.environ.get("HW_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DHW_SA_MIN_BLOCKS_D=8
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + srcs
+def _compile_one(args):
+    cmd, obj = args
     subprocess.check_call(cmd)
-    os.replace(LIB + ".tmp", LIB)
-    return LIB
+    return obj
+
+
+def build(force=False, verbose=False, out=None):
+    """compile every CUDA source (one nvcc process per file, in parallel) and link them into one shared library; returns its path.
+    Objects are kept under build/obj/<flags> and reused while the source, the headers and the flags are unchanged."""
+    import hashlib
+    from concurrent.futures import ThreadPoolExecutor
+    lib = out or LIB
+    if not force and out is None and not needs_build():
+        return LIB
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    extra = os.environ.get("HW_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DHW_SA_MIN_BLOCKS_D=8
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+    objroot = os.path.join(os.path.dirname(HERE), "build", "obj")
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS if os.path.exists(os.path.join(CSRC, h)))
+    hdr_t = max(hdr_t, os.path.getmtime(os.path.abspath(__file__)))
+    jobs, objs = [], []
+    for s in srcs:
+        # per-file experiment flags: HW_NVCC_EXTRA_HW_MA_TPE="-DHW_TPE_ONLY=5 ..." touches that object only
+        fflags = cflags + os.environ.get("HW_NVCC_EXTRA_" + s[:-3].upper(), "").split()
+        objdir = os.path.join(objroot, hashlib.sha1(" ".join(fflags).encode()).hexdigest()[:12])
+        os.makedirs(objdir, exist_ok=True)
+        src, obj = os.path.join(CSRC, s), os.path.join(objdir, s[:-3] + ".o")
+        objs.append(obj)
+        fresh = os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t)
+        if verbose or not fresh or (force and not os.environ.get("HW_BUILD_REUSE_OBJECTS")):
+            jobs.append(([_nvcc()] + fflags + ["-c", "-o", obj, src], obj))
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        list(ex.map(_compile_one, jobs))
+    subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib + ".tmp"] + objs)
+    os.replace(lib + ".tmp", lib)
+    return lib
 
 
 if __name__ == "__main__":

@@ -66,6 +66,20 @@ __device__ __forceinline__ void tset_if(bool p, double &x, double c) { dset_if(p
 __device__ __forceinline__ double tclamp(double x, const double lo, const double hi) { return py_clamp(x, lo, hi); }
 #endif
 
+// HW_TPE_PROF (experiment builds only): per-phase clock64() accounting of the step, summed over the warps into g_tpe_prof and read
+// back through hw_debug_tpe_prof (scripts/tpe_phase_profile.py).  Off: the macros vanish.
+#ifdef HW_TPE_PROF
+__device__ unsigned long long g_tpe_prof[16];
+struct TpeProf { long long t[12]; long long last; };
+#define TPE_PROF_ARG , TpeProf &prof
+#define TPE_PROF_PASS , prof
+#define TPE_MARK(k) do { const long long now_ = clock64(); prof.t[k] += now_ - prof.last; prof.last = now_; } while (0)
+#else
+#define TPE_PROF_ARG
+#define TPE_PROF_PASS
+#define TPE_MARK(k) do { } while (0)
+#endif
+
 struct TpeOb {  // this thread's column of the warp-private obstacle region
     double *base;
     __device__ __forceinline__ double &operator()(int k, int f) const { return base[(k * O_NF + f) * 32]; }
@@ -210,8 +224,9 @@ __device__ __forceinline__ uint32_t tpe_pack_rect(int x, int y) { return ((uint3
 template <int A, bool CONT, bool EXACT>
 __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const TpeOb ob, const int K, const MaConsts &C, const double dt,
                                              const bool inf_obs, const uint32_t (&amask)[A], const double (&a0)[A], const double (&a1)[A],
-                                             const uint64_t seed, const uint64_t env_id, uint32_t &done)
+                                             const uint64_t seed, const uint64_t env_id, uint32_t &done TPE_PROF_ARG)
 {
+    TPE_MARK(1);
     h.tick += 1;
     if (h.tick >= (uint32_t)C.timeout_tick) done |= (1u << A) - 1u;  // highway_core.py:276-277
 
@@ -259,6 +274,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         c.steer[a] = tclamp(c.steer[a], -30.0, 30.0);
     }
 
+    TPE_MARK(2);
     // ---- car updates in id order against last tick's leader (agent.py:79-165): a car subtracts the leader's velocity "as it is
     //      now" (agent.py:147-151) - its new value for the cars after it in id order, its old one for those before ----
     // Written as three passes over the cars (velocity and steering, angular velocity, position), each a straight line of A
@@ -296,6 +312,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         }
         c.b[a] = b;
     }
+    TPE_MARK(3);
     double lv = c.vx[0];  // the leader's velocity "as it is now" for the cars after it: its new value
 #pragma unroll
     for (int j = 1; j < A; ++j) tmov_if(L == j, lv, c.vx[j]);
@@ -307,6 +324,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         tset_if(!(c.steer[a] != 0.0), ang[a], 0.0);
         if (!CONT) c.vy[a] = ang[a];  // agent.py:144: velocity.y = angular_velocity (discrete update only)
     }
+    TPE_MARK(4);
 #pragma unroll
     for (int a = 0; a < A; ++a) {
         double lva = lv_old;
@@ -329,6 +347,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
     }
     const double lvdt = dmul(lv, dt);  // last tick's leader, this tick's velocity
 
+    TPE_MARK(5);
     // ---- leader / last election: stable sort of the cars by x, descending (highway_core.py:294-297).  In the reference it follows
     //      the obstacle updates, but it only reads the cars, which are final by now ----
     int lead = 0;
@@ -351,6 +370,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
     //      are in registers it is tested for a spawn / retire and against the cars' rects (an obstacle that is retired below is
     //      more than 14 m behind the last car, so testing it too cannot add an overlap in a consistent frame; the exact count
     //      walks the final list in any case) ----
+    TPE_MARK(6);
     const double thr = dsub(dsub(-2.375, plead), 2.0);
     const uint32_t newest_mask = (1u << h.newest[0]) | (1u << h.newest[1]) | (1u << h.newest[2]);  // 31 = retired: matches no slot
     bool want = false;
@@ -376,6 +396,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
 #pragma unroll
         for (int a = 0; a < A; ++a) nohit = min(nohit, (pa[a] - pb) & kRectMask);
     }
+    TPE_MARK(7);
     h.ofresh = 0;  // every live obstacle has now written its rect
     if (inf_obs && want) {
         const TpeSlots r = tpe_spawn_retire(TpeSlots{h.nobs, h.olane, h.ofresh, h.newest[0], h.newest[1], h.newest[2], h.spawn_ctr, h.flags},
@@ -397,6 +418,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
     uint32_t hit = 0;
     if (nohit == 0u) hit = tpe_collide_exact<A>(h, c, ob);
     done |= hit;
+    TPE_MARK(8);
     return hit;
 }
 
@@ -494,6 +516,11 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
     uint32_t amask[A];
     double a0[A], a1[A];
     const uint64_t env_id = env_id0 + (uint64_t)i;
+#ifdef HW_TPE_PROF
+    TpeProf prof;
+    for (int j = 0; j < 12; ++j) prof.t[j] = 0;
+    prof.last = clock64();
+#endif
     if (live) {
         ma_load_head(h, S, i, n);
         // is_done persists until reset() (highway_core.py:239, :420): with HW_FLAG_NO_AUTORESET a car that finished in an earlier
@@ -532,7 +559,7 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
         for (int t = 0; t < C.ticks_per_step; ++t) {
             if (HW_TPE_SYNC == 1) __syncthreads();
             if (run) {
-                hit = tpe_tick<A, CONT, EXACT>(h, c, ob, K, C, dt, inf_obs, amask, a0, a1, seed, env_id, done);
+                hit = tpe_tick<A, CONT, EXACT>(h, c, ob, K, C, dt, inf_obs, amask, a0, a1, seed, env_id, done TPE_PROF_PASS);
                 if (done) run = false;  // highway_env.py:85-86: the step ends with the first tick that finishes a car
             }
         }
@@ -540,11 +567,12 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
 #else
     if (live) {
         for (int t = 0; t < C.ticks_per_step; ++t) {
-            hit = tpe_tick<A, CONT, EXACT>(h, c, ob, K, C, dt, inf_obs, amask, a0, a1, seed, env_id, done);
+            hit = tpe_tick<A, CONT, EXACT>(h, c, ob, K, C, dt, inf_obs, amask, a0, a1, seed, env_id, done TPE_PROF_PASS);
             if (done) break;  // highway_env.py:85-86: the step ends with the first tick that finishes a car
         }
     }
 #endif
+    TPE_MARK(9);   // barrier waits and the idle ticks of finished environments (the ticks themselves are marked inside)
     if (live) {
 
         // rewards of the step (Scenario.rewards of the last tick that ran, simple_base.py:65-80): -250 for a car that collided in it,
@@ -594,6 +622,7 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
             S.obst[(int64_t)k * n + i] = make_float4((float)ob(k, O_PX), (float)ob(k, O_RX), (float)ob(k, O_VX), (float)ob(k, O_IV));
     }
 
+    TPE_MARK(10);
     // observation rows: staged in the warp's (now free) shared region, kPass cars at a time, and streamed out 8 bytes per lane -
     // consecutive lanes write consecutive addresses of the environments' contiguous [A][4A+14] blocks
     constexpr int kPass = (kTpeWarpDoubles / 32) / D2 < A ? (kTpeWarpDoubles / 32) / D2 : A;  // cars per pass that fit the region
@@ -621,6 +650,13 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
         }
     }
 
+    TPE_MARK(11);
+#ifdef HW_TPE_PROF
+    if (lane_id == 0) {
+        for (int j = 0; j < 12; ++j) atomicAdd(&g_tpe_prof[j], (unsigned long long)prof.t[j]);
+        atomicAdd(&g_tpe_prof[12], 1ull);
+    }
+#endif
     if (stats) {
         if (__any_sync(0xffffffffu, acc[0] != 0)) {
 #pragma unroll
@@ -657,6 +693,9 @@ int ma_tpe_launch_step(const HwMaState *st, const void *actions, const HwMaOut *
 {
     MaPtrs S;
     S.cars = st->cars; S.obst = reinterpret_cast<float4 *>(st->obst); S.head = st->head; S.A = st->num_agents; S.K = st->num_slots;
+#ifdef HW_TPE_ONLY   // experiment builds: one instantiation instead of eight (compile time)
+    if (S.A == HW_TPE_ONLY) return ma_tpe_launch_a<HW_TPE_ONLY>(S, actions, out, C_, seed, env_id0, n, flags, stream);
+#else
     switch (S.A) {
     case 1: return ma_tpe_launch_a<1>(S, actions, out, C_, seed, env_id0, n, flags, stream);
     case 2: return ma_tpe_launch_a<2>(S, actions, out, C_, seed, env_id0, n, flags, stream);
@@ -667,7 +706,20 @@ int ma_tpe_launch_step(const HwMaState *st, const void *actions, const HwMaOut *
     case 7: return ma_tpe_launch_a<7>(S, actions, out, C_, seed, env_id0, n, flags, stream);
     case 8: return ma_tpe_launch_a<8>(S, actions, out, C_, seed, env_id0, n, flags, stream);
     }
+#endif
     return HW_E_BADARG;
 }
 
 }  // namespace hw
+
+#ifdef HW_TPE_PROF
+extern "C" int hw_debug_tpe_prof(unsigned long long *host16, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(host16, hw::g_tpe_prof, sizeof(hw::g_tpe_prof));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[16] = {0};
+        e = cudaMemcpyToSymbol(hw::g_tpe_prof, z, sizeof(z));
+    }
+    return (int)e;
+}
+#endif
