@@ -55,15 +55,32 @@ __device__ __forceinline__ void tmov_if_nz(uint32_t w, double &x, double y)
 __device__ __forceinline__ void tset_if(bool p, double &x, double c) { tmov_if(p, x, c); }
 __device__ __forceinline__ double tclamp(double x, const double lo, const double hi)
 {
-    tset_if(hi < x, x, hi);
-    tset_if(!(x > lo), x, lo);
+    const bool over = hi < x, under = !(x > lo);
+    tset_if(over, x, hi);
+    tset_if(under, x, lo);
     return x;
 }
 #else
 __device__ __forceinline__ void tmov_if(bool p, double &x, double y) { dmov_if(p, x, y); }
 __device__ __forceinline__ void tmov_if_nz(uint32_t w, double &x, double y) { dmov_if_nz(w, x, y); }
 __device__ __forceinline__ void tset_if(bool p, double &x, double c) { dset_if(p, x, c); }
-__device__ __forceinline__ double tclamp(double x, const double lo, const double hi) { return py_clamp(x, lo, hi); }
+#ifndef HW_TPE_CLAMP
+#define HW_TPE_CLAMP 1
+#endif
+// python max(lo, min(x, hi)).  Both tests read the ORIGINAL x (x > hi implies x > lo, so the second test cannot fire after the first
+// moved x to hi; a NaN fails the first and passes the second either way): the two DSETP issue back to back instead of the second
+// one waiting for the first conditional move - a DSETP takes ~20 cycles to deliver its predicate on B200, a dependent pair ~57.
+__device__ __forceinline__ double tclamp(double x, const double lo, const double hi)
+{
+#if HW_TPE_CLAMP
+    const bool over = hi < x, under = !(x > lo);
+    dset_if(over, x, hi);
+    dset_if(under, x, lo);
+    return x;
+#else
+    return py_clamp(x, lo, hi);
+#endif
+}
 #endif
 
 // HW_TPE_PROF (experiment builds only): per-phase clock64() accounting of the step, summed over the warps into g_tpe_prof and read
@@ -211,13 +228,30 @@ __device__ __forceinline__ uint32_t tpe_collide_exact(MaHead &h, const TpeCars<A
 }
 
 // The per-tick overlap FILTER works on rects packed into one word, x in the upper and y in the lower 16 bits.  With
-// dx = ax - bx + 75 and dy = ay - by + 37, A overlaps B iff 0 <= dx <= 150 and 0 <= dy <= 74.  Adding 105 to dx and 53 to dy makes
-// both upper bounds 2^k - 1 (255, 127), so T = ((dx + 105) << 16) + (dy + 53) has no bit under the mask 0xFF00FF80 iff both hold:
-// a negative dy borrows into its own high bits (and decrements dx, which then fails or stays valid - dy has failed already), a
-// negative or large dx sets bits above its low eight.  (Fields cannot alias while |dx| < 65 000 px, i.e. within 2 000 m: an
-// episode moves a vehicle by 1 200 m at most.)  min() over the masked words of all pairs is zero iff some pair overlaps.
+// dx = ax - bx + 75 and dy = ay - by + 37, A overlaps B iff 0 <= dx <= 150 and 0 <= dy <= 74, i.e. iff dx <= 150, dy <= 74 AND the same
+// two bounds with the roles of A and B exchanged (dx' = 150 - dx, dy' = 74 - dy).  Adding 105 to dx and 53 to dy makes the upper
+// bounds 2^k - 1 (255, 127), so T = ((dx + 105) << 16) + (dy + 53) has no bit under the mask 0xFF00FF80 iff both upper bounds hold
+// (and the value is not below -105 / -53); T | T' has none iff all four hold: the filter is EXACT.  (One word alone also passes a
+// vehicle up to 180 px - 5.6 m - ahead in the same lane, which the start grid's (10, L) / (5, L) pairs are: the exact count then
+// ran for 13 of 32 lanes in a third of all ticks - 11 % of the kernel's instructions.)  A negative field borrows into its own high
+// bits (and from the x field, which then fails or stays valid - the pair has failed already).  Fields cannot alias while
+// |dx| < 65 000 px, i.e. within 2 000 m: an episode moves a vehicle by 1 200 m at most.  min() over the masked words of all pairs
+// is zero iff some pair overlaps.
+#ifndef HW_TPE_FILTER2
+#define HW_TPE_FILTER2 1   // 0: the one-word (superset) filter
+#endif
 constexpr uint32_t kRectMask = 0xFF00FF80u;
 constexpr uint32_t kRectBias = (105u << 16) + 53u;
+constexpr uint32_t kRectSize = (75u << 16) + 37u;
+// pa = pack(ax + 75, ay + 37) of a car, pb = pack(bx, by) of the other rect: the masked test word
+__device__ __forceinline__ uint32_t tpe_filter_word(uint32_t pa, uint32_t pb)
+{
+#if HW_TPE_FILTER2
+    return ((pa - pb + kRectBias) | (pb - pa + (2u * kRectSize + kRectBias))) & kRectMask;
+#else
+    return (pa - pb + kRectBias) & kRectMask;
+#endif
+}
 __device__ __forceinline__ uint32_t tpe_pack_rect(int x, int y) { return ((uint32_t)x << 16) + (uint32_t)y; }
 
 // one world.act() followed by Scenario.rewards() (highway_core.py:245-399, simple_base.py:65-80); returns the cars that collided
@@ -232,6 +266,69 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
 
     // ---- actions for every car in id order (highway_core.py:280-281, :110-188): maintain() of car a sees the lanes the cars
     //      before it have just switched to and the old lanes of the cars after it - program order ----
+#ifndef HW_TPE_ACT
+#define HW_TPE_ACT 1
+#endif
+#if HW_TPE_ACT
+    if (CONT) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            c.acc[a] = tclamp(dadd(c.acc[a], a0[a]), -5.0, 5.0);
+            c.steer[a] = tclamp(dadd(c.steer[a], a1[a]), -30.0, 30.0);
+        }
+    } else {
+        // amask = the mode bit the action asks for; it fires when not yet set.  The two modes of a pair exclude each other, so
+        // setting the bit and clearing its partner is the identity when nothing fires.  Lane changes first (integers only): the
+        // maintain() of car a below wants the NEW lane of the cars before it and the OLD lane of the cars after it (its own lane
+        // does not change in a tick in which its MAINTAIN fires).
+        uint32_t fire[A], anyfire = 0;
+        int ln_old[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const uint32_t am = amask[a];
+            const uint32_t apair = am | ((am & (kBitLeft | kBitDoAcc)) << 1) | ((am & (kBitRight | kBitDoMaint)) >> 1);
+            fire[a] = am & ~c.b[a];
+            anyfire |= fire[a];
+            c.b[a] = (c.b[a] & ~apair) | am;
+            ln_old[a] = c.ln[a];
+            const int dl = (int)((fire[a] >> 19) & 1u) - (int)((fire[a] >> 18) & 1u);  // RIGHT +1, LEFT -1, only when it fires
+            c.ln[a] = min(max(c.ln[a] + dl, 1), 3);
+            c.acc[a] = tclamp(c.acc[a], -5.0, 5.0);
+            c.steer[a] = tclamp(c.steer[a], -30.0, 30.0);
+        }
+        if (anyfire & kBitDoMaint) {
+            // maintain(): cruise = velocity of the nearest vehicle strictly ahead in the lane, else the car's own.  all_obstacles
+            // iterates the cars (id order) and then the obstacles (insertion order); the first wins ties.  The searches of the A cars
+            // are evaluated side by side - A independent dependency chains, one pass over the obstacle list - and only the cars whose
+            // MAINTAIN fired keep the result.  (One search after the other, each behind its own branch, was a chain of
+            // compare -> conditional move links of ~28 cycles each that nothing overlapped.)
+            double bpx[A], bvx[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) { bpx[a] = tpe_inf(); bvx[a] = dcopy(c.vx[a]); }
+#pragma unroll
+            for (int j = 0; j < A; ++j) {
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    if (j == a) continue;
+                    const int lane_j = (j < a) ? c.ln[j] : ln_old[j];
+                    const bool take = (lane_j == c.ln[a]) & (c.px[j] > c.px[a]) & (c.px[j] < bpx[a]);
+                    tmov_if(take, bpx[a], c.px[j]); tmov_if(take, bvx[a], c.vx[j]);
+                }
+            }
+            for (int k = 0; k < (int)h.nobs; ++k) {
+                const int lane_k = ob_lane(h, k);
+                const double opx = ob(k, O_PX), ovx = ob(k, O_VX);
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    const bool take = (lane_k == c.ln[a]) & (opx > c.px[a]) & (opx < bpx[a]);
+                    tmov_if(take, bpx[a], opx); tmov_if(take, bvx[a], ovx);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < A; ++a) tmov_if_nz(fire[a] & kBitDoMaint, c.cruise[a], bvx[a]);
+        }
+    }
+#else
     const uint32_t live = live_mask(h.nobs);
 #pragma unroll
     for (int a = 0; a < A; ++a) {
@@ -274,6 +371,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         c.steer[a] = tclamp(c.steer[a], -30.0, 30.0);
     }
 
+#endif
     TPE_MARK(2);
     // ---- car updates in id order against last tick's leader (agent.py:79-165): a car subtracts the leader's velocity "as it is
     //      now" (agent.py:147-151) - its new value for the cars after it in id order, its old one for those before ----
@@ -336,8 +434,11 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         else      py = dsub(py, dmul(dmul(dmul(ang[a], kRad2Deg), dt), dt));
         px = dsub(px, dmul(lva, dt));
         tset_if(L == a, px, 10.0);
-        tset_if(7.0 < py, py, 7.0);   // if y < 1: y = 1 elif y > 6: y = min(y, 7)
-        tset_if(py < 1.0, py, 1.0);
+        {   // if y < 1: y = 1 elif y > 6: y = min(y, 7); both tests on the value before either move (they exclude each other)
+            const bool over = 7.0 < py, under = py < 1.0;
+            tset_if(over, py, 7.0);
+            tset_if(under, py, 1.0);
+        }
         c.rx[a] = dadd(c.rx[a], vdt);
         c.px[a] = px; c.py[a] = py;
         if (CONT) {
@@ -392,9 +493,9 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         const double orx2 = dadd(orx, odt);
         ob(k, O_VX) = v; ob(k, O_PX) = opx; ob(k, O_RX) = orx2;
         want = want | ((((newest_mask >> k) & 1u) != 0u) & (opx < -2.375)) | (dsub(orx2, last_rx) < thr);
-        const uint32_t pb = tpe_pack_rect(rect_x(opx), 80 * lane - 59) - kRectBias;  // y = 21 + 80 * (lane - 1)
+        const uint32_t pb = tpe_pack_rect(rect_x(opx), 80 * lane - 59);  // y = 21 + 80 * (lane - 1)
 #pragma unroll
-        for (int a = 0; a < A; ++a) nohit = min(nohit, (pa[a] - pb) & kRectMask);
+        for (int a = 0; a < A; ++a) nohit = min(nohit, tpe_filter_word(pa[a], pb));
     }
     TPE_MARK(7);
     h.ofresh = 0;  // every live obstacle has now written its rect
@@ -405,7 +506,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         h.spawn_ctr = r.spawn_ctr; h.flags = r.flags;
         if (h.ofresh) {  // a slot spawned in this tick carries pygame's default rect (0, 0, 76, 38) into check_collisions
 #pragma unroll
-            for (int a = 0; a < A; ++a) nohit = min(nohit, (pa[a] + kRectBias) & kRectMask);
+            for (int a = 0; a < A; ++a) nohit = min(nohit, tpe_filter_word(pa[a], 0u));
         }
     }
 
@@ -413,13 +514,48 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
 #pragma unroll
     for (int a = 0; a < A; ++a) {
 #pragma unroll
-        for (int j = a + 1; j < A; ++j) nohit = min(nohit, (pa[a] - pa[j] + (tpe_pack_rect(75, 37) + kRectBias)) & kRectMask);
+        for (int j = a + 1; j < A; ++j) nohit = min(nohit, tpe_filter_word(pa[a], pa[j] - kRectSize));
     }
     uint32_t hit = 0;
     if (nohit == 0u) hit = tpe_collide_exact<A>(h, c, ob);
     done |= hit;
     TPE_MARK(8);
     return hit;
+}
+
+// N normalisations (norm_f64: float32 cast, clip, (v - lo) / (hi - lo) in float64, float32 cast) evaluated stage by stage.  One value
+// is a chain of nine dependent instructions (~95 cycles with the three conversions); written one value after the other ptxas
+// emitted the 170 chains of a step back to back (a third of the kernel's stall samples sat in the epilogue).  Side by side the
+// N chains of a batch overlap.  BND: 0 = +-5, 1 = +-30, 2 = 0..1200, 3 = 0..8, 4 = +-60, 5 = +-8, 6 = +-20.
+#ifndef HW_TPE_EPI
+#define HW_TPE_EPI 1
+#endif
+__device__ __forceinline__ constexpr double tpe_bnd_lo(int b) { return b == 0 ? -5.0 : b == 1 ? -30.0 : b == 2 ? 0.0 : b == 3 ? 0.0 : b == 4 ? -60.0 : b == 5 ? -8.0 : -20.0; }
+__device__ __forceinline__ constexpr double tpe_bnd_hi(int b) { return b == 0 ? 5.0 : b == 1 ? 30.0 : b == 2 ? 1200.0 : b == 3 ? 8.0 : b == 4 ? 60.0 : b == 5 ? 8.0 : 20.0; }
+template <int N, int B0, int B1 = 0, int B2 = 0, int B3 = 0, int B4 = 0, int B5 = 0>
+__device__ __forceinline__ void tpe_norm_n(const double (&raw)[N], float (&out)[N])
+{
+    constexpr int B[6] = {B0, B1, B2, B3, B4, B5};
+    static_assert(N <= 6, "batch size");
+#if HW_TPE_EPI
+    float v[N];
+    double x[N], q0[N], e[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = (float)raw[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i], (float)tpe_bnd_lo(B[i])), (float)tpe_bnd_hi(B[i]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = dsub((double)v[i], tpe_bnd_lo(B[i]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) q0[i] = dmul(x[i], 1.0 / (tpe_bnd_hi(B[i]) - tpe_bnd_lo(B[i])));
+#pragma unroll
+    for (int i = 0; i < N; ++i) e[i] = __fma_rn(-q0[i], tpe_bnd_hi(B[i]) - tpe_bnd_lo(B[i]), x[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = (float)__fma_rn(e[i], 1.0 / (tpe_bnd_hi(B[i]) - tpe_bnd_lo(B[i])), q0[i]);
+#else
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = norm_f64(raw[i], tpe_bnd_lo(B[i]), tpe_bnd_hi(B[i]));
+#endif
 }
 
 // MultiAgentEnv._get_obs_norm (highway_env.py:139-149) of one value: see norm_f64
@@ -452,9 +588,19 @@ __device__ __forceinline__ uint32_t tpe_observe_obstacles(MaHead &h, const TpeCa
         }
         if (none) { h.flags |= 2u; nolane |= 1u << l; }
 #pragma unroll
-        for (int a = 0; a < A; ++a) {
-            odx[a][l] = none ? 0.5f : norm_f64(dsub(brx[a], c.rx[a]), -60.0, 60.0);
-            odv[a][l] = none ? 0.5f : norm_f64(dsub(bvx[a], c.vx[a]), -20.0, 20.0);
+        for (int a0 = 0; a0 < A; a0 += 2) {  // two cars = four chains side by side
+            if (a0 + 1 < A) {
+                const double raw[4] = {dsub(brx[a0], c.rx[a0]), dsub(bvx[a0], c.vx[a0]), dsub(brx[a0 + 1], c.rx[a0 + 1]), dsub(bvx[a0 + 1], c.vx[a0 + 1])};
+                float o[4];
+                tpe_norm_n<4, 4, 6, 4, 6>(raw, o);
+                odx[a0][l] = none ? 0.5f : o[0]; odv[a0][l] = none ? 0.5f : o[1];
+                odx[a0 + 1][l] = none ? 0.5f : o[2]; odv[a0 + 1][l] = none ? 0.5f : o[3];
+            } else {
+                const double raw[2] = {dsub(brx[a0], c.rx[a0]), dsub(bvx[a0], c.vx[a0])};
+                float o[2];
+                tpe_norm_n<2, 4, 6>(raw, o);
+                odx[a0][l] = none ? 0.5f : o[0]; odv[a0][l] = none ? 0.5f : o[1];
+            }
         }
     }
     return nolane;
@@ -466,24 +612,35 @@ __device__ __forceinline__ void tpe_observe_row(const TpeCars<A> &c, const int a
                                                 const uint32_t nolane, Put put)
 {
     constexpr int S = A + 2;
-    put(0, make_float2(norm_f64(c.acc[a], -5.0, 5.0), norm_f64(c.steer[a], -30.0, 30.0)));
-    put(1, make_float2(norm_f64(c.rx[a], 0.0, 1200.0), norm_f64(c.py[a], 0.0, 8.0)));
-    put(2 + S, make_float2(norm_f64(c.vx[a], -20.0, 20.0), norm_f64(c.vy[a], -20.0, 20.0)));
+    {   // the car itself: acc, steer, raw x, y, vx, vy
+        const double raw[6] = {c.acc[a], c.steer[a], c.rx[a], c.py[a], c.vx[a], c.vy[a]};
+        float o[6];
+        tpe_norm_n<6, 0, 1, 2, 3, 6, 6>(raw, o);
+        put(0, make_float2(o[0], o[1]));
+        put(1, make_float2(o[2], o[3]));
+        put(2 + S, make_float2(o[4], o[5]));
+    }
 #pragma unroll
     for (int j = 0; j < A; ++j) {  // other cars: car j goes to slot j - (j > a)
         if (j == a) continue;
         const int sl = j - (j > a ? 1 : 0);
-        put(2 + sl, make_float2(norm_f64(dsub(c.rx[j], c.rx[a]), -60.0, 60.0), norm_f64(dsub(c.py[j], c.py[a]), -8.0, 8.0)));
-        put(3 + S + sl, make_float2(norm_f64(dsub(c.vx[j], c.vx[a]), -20.0, 20.0), norm_f64(dsub(c.vy[j], c.vy[a]), -20.0, 20.0)));
+        const double raw[4] = {dsub(c.rx[j], c.rx[a]), dsub(c.py[j], c.py[a]), dsub(c.vx[j], c.vx[a]), dsub(c.vy[j], c.vy[a])};
+        float o[4];
+        tpe_norm_n<4, 4, 5, 6, 6>(raw, o);
+        put(2 + sl, make_float2(o[0], o[1]));
+        put(3 + S + sl, make_float2(o[2], o[3]));
     }
+    {   // obstacles: slot A - 1 + lane; the lateral offsets to the three lane centres and the (common) relative lateral velocity
+        const double raw[4] = {dsub(lane_centre(0), c.py[a]), dsub(lane_centre(1), c.py[a]), dsub(lane_centre(2), c.py[a]), dsub(0.0, c.vy[a])};
+        float o[4];
+        tpe_norm_n<4, 5, 5, 5, 6>(raw, o);
 #pragma unroll
-    for (int l = 0; l < 3; ++l) {  // obstacles: slot A - 1 + lane
-        const int s = A - 1 + l;
-        const bool none = ((nolane >> l) & 1u) != 0u;
-        const float dy = none ? 0.5f : norm_f64(dsub(lane_centre(l), c.py[a]), -8.0, 8.0);
-        const float dvy = none ? 0.5f : norm_f64(dsub(0.0, c.vy[a]), -20.0, 20.0);
-        put(2 + s, make_float2(odx[a][l], dy));
-        put(3 + S + s, make_float2(odv[a][l], dvy));
+        for (int l = 0; l < 3; ++l) {
+            const int s = A - 1 + l;
+            const bool none = ((nolane >> l) & 1u) != 0u;
+            put(2 + s, make_float2(odx[a][l], none ? 0.5f : o[l]));
+            put(3 + S + s, make_float2(odv[a][l], none ? 0.5f : o[3]));
+        }
     }
 }
 
@@ -644,9 +801,17 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
         const int per_env = cn * D2;                  // compile-time after unrolling: the division below is a multiply and a shift
         const int nv = (n - i0 < 32) ? (int)(n - i0) : 32;   // environments of this warp that exist
         float2 *dst = out2 + i0 * (int64_t)(A * D2) + c0 * D2;
-        for (int idx = lane_id; idx < 32 * per_env; idx += 32) {
-            const int e = idx / per_env, q = idx - e * per_env;
-            if (e < nv) dst[e * (A * D2) + q] = stage[idx];
+        if (nv == 32) {  // independent iterations, unrolled so that their LDS -> STG chains overlap
+#pragma unroll 6
+            for (int idx = lane_id; idx < 32 * per_env; idx += 32) {
+                const int e = idx / per_env, q = idx - e * per_env;
+                dst[e * (A * D2) + q] = stage[idx];
+            }
+        } else {
+            for (int idx = lane_id; idx < 32 * per_env; idx += 32) {
+                const int e = idx / per_env, q = idx - e * per_env;
+                if (e < nv) dst[e * (A * D2) + q] = stage[idx];
+            }
         }
     }
 
