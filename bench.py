@@ -260,7 +260,7 @@ def side_measure(kind, continuous, n, dev, rank, args, steps=100, warmup=5, agen
         out.update({"agents": A, "agent_steps_per_s": A * n / t, "mean_live_obstacles": live,
                     "live_slot_bytes_per_env_step": b_live, "roofline_frac_live_slots": n * b_live / t / 1e9 / peak,
                     "dropped_spawns": st.get("dropped_spawns"), "mean_episode_length": st.get("mean_length"),
-                    "kernel": "ma_tpe_step_kernel (thread per environment, cars in registers)" if n >= 24576
+                    "kernel": "ma_tpe_step_kernel (thread per environment, cars in registers)" if n >= 16384
                               else "ma_grp_step_kernel (lane per car)"})
     del env, acts, fb
     torch.cuda.empty_cache()
@@ -471,7 +471,7 @@ def main():
                        "parallelism": "independent env shards, %d rank(s), no data-path collective" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(info["kind"], info["continuous"], n), "peak_source": peak_src,
-                         "kernel": "sa_step_kernel" if info["kind"] == "sa" else ("ma_tpe_step_kernel" if n >= 24576 else "ma_grp_step_kernel"),
+                         "kernel": "sa_step_kernel" if info["kind"] == "sa" else ("ma_tpe_step_kernel" if n >= 16384 else "ma_grp_step_kernel"),
                          "algorithmic_bytes_per_env_step": bps,
                          "avg_launch_us": avg_launch_s * 1e6, "min_launch_us": float(dev_ms.min()) * 1e3},
             "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks,

@@ -88,10 +88,19 @@ __device__ __forceinline__ void dset_if(bool p, double &x, double c)
 // python max(lo, min(x, hi)): min keeps x unless hi < x; max keeps lo unless the inner value is > lo.  (Spelled with
 // conditional moves: NVVM turns the C++ ternary `(x > lo) ? x : lo` into max.f64, whose NaN-aware expansion on sm_100a is
 // six instructions.)
+#ifndef HW_CLAMP_PAR
+#define HW_CLAMP_PAR 0   // 1: both tests on the original x (they exclude each other), so the two DSETP issue back to back
+#endif
 __device__ __forceinline__ double py_clamp(double x, const double lo, const double hi)
 {
+#if HW_CLAMP_PAR
+    const bool over = hi < x, under = !(x > lo);
+    dset_if(over, x, hi);
+    dset_if(under, x, lo);
+#else
     dset_if(hi < x, x, hi);
     dset_if(!(x > lo), x, lo);
+#endif
     return x;
 }
 

@@ -187,12 +187,13 @@ static int ma_launch_step(const HwMaState *st, const void *actions, const HwMaOu
     MaConsts C_;
     C_.dt = P->dt; C_.k30dt = 30.0 * P->dt; C_.ticks_per_step = P->ticks_per_step; C_.timeout_tick = P->timeout_tick;
     // two layouts of the same step (identical results): a thread per environment with the cars in registers (hw_ma_tpe.cu: fewest
-    // instructions per environment, 283 us against 371 us at 262 144 environments) or a lane per car (hw_ma_grp.cu: five times the
-    // threads, the better fit for the smallest batches - 41 us against 51 us at 16 384; the crossover is at ~24 576)
+    // instructions per environment, 252 us against 379 us at 262 144 environments) or a lane per car (hw_ma_grp.cu: five times the
+    // threads, the better fit for the smallest batches; the two meet at 16 384 environments - 41 us each - and at 32 768 it is 50 us
+    // against 66 us)
     if (st->num_agents > kMaxA && (flags & HW_FLAG_MA_LANE_PER_CAR)) return HW_E_BADARG;  // the extension (6..8 cars) has one kernel
     // measured crossover (B200): the lane-per-car kernel always spends five lanes per environment, so the fewer the cars the
-    // earlier the thread-per-environment kernel wins - at every size for one or two cars, from 8 192 / 16 384 / 24 576
-    // environments for three / four / five
+    // earlier the thread-per-environment kernel wins - at every size for one or two cars, from HW_MA_TPE_MIN_ENVS
+    // environments for five cars, a third / two thirds of that for three / four
     const int64_t tpe_min = (st->num_agents <= 2) ? 0 : (int64_t)(HW_MA_TPE_MIN_ENVS / 3) * (st->num_agents - 2);
     const bool tpe = (flags & HW_FLAG_MA_THREAD_PER_ENV) || st->num_agents > kMaxA
                      || (!(flags & HW_FLAG_MA_LANE_PER_CAR) && n >= tpe_min);

@@ -87,6 +87,41 @@ __device__ __forceinline__ float norm_f64(double raw, const double lo, const dou
     return (float)__fma_rn(__fma_rn(-q0, c, x), rc, q0);
 }
 
+// N normalisations (norm_f64: float32 cast, clip, (v - lo) / (hi - lo) in float64, float32 cast) evaluated stage by stage.  One value
+// is a chain of nine dependent instructions (~95 cycles with the three conversions); written one value after the other ptxas
+// emitted the 170 chains of a step back to back (a third of the kernel's stall samples sat in the epilogue).  Side by side the
+// N chains of a batch overlap.  BND: 0 = +-5, 1 = +-30, 2 = 0..1200, 3 = 0..8, 4 = +-60, 5 = +-8, 6 = +-20.
+#ifndef HW_MA_NORM_BATCH
+#define HW_MA_NORM_BATCH 1
+#endif
+__device__ __forceinline__ constexpr double ma_bnd_lo(int b) { return b == 0 ? -5.0 : b == 1 ? -30.0 : b == 2 ? 0.0 : b == 3 ? 0.0 : b == 4 ? -60.0 : b == 5 ? -8.0 : -20.0; }
+__device__ __forceinline__ constexpr double ma_bnd_hi(int b) { return b == 0 ? 5.0 : b == 1 ? 30.0 : b == 2 ? 1200.0 : b == 3 ? 8.0 : b == 4 ? 60.0 : b == 5 ? 8.0 : 20.0; }
+template <int N, int B0, int B1 = 0, int B2 = 0, int B3 = 0, int B4 = 0, int B5 = 0>
+__device__ __forceinline__ void ma_norm_n(const double (&raw)[N], float (&out)[N])
+{
+    constexpr int B[6] = {B0, B1, B2, B3, B4, B5};
+    static_assert(N <= 6, "batch size");
+#if HW_MA_NORM_BATCH
+    float v[N];
+    double x[N], q0[N], e[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = (float)raw[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i], (float)ma_bnd_lo(B[i])), (float)ma_bnd_hi(B[i]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = dsub((double)v[i], ma_bnd_lo(B[i]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) q0[i] = dmul(x[i], 1.0 / (ma_bnd_hi(B[i]) - ma_bnd_lo(B[i])));
+#pragma unroll
+    for (int i = 0; i < N; ++i) e[i] = __fma_rn(-q0[i], ma_bnd_hi(B[i]) - ma_bnd_lo(B[i]), x[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = (float)__fma_rn(e[i], 1.0 / (ma_bnd_hi(B[i]) - ma_bnd_lo(B[i])), q0[i]);
+#else
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = norm_f64(raw[i], ma_bnd_lo(B[i]), ma_bnd_hi(B[i]));
+#endif
+}
+
 
 // G lanes per environment (hw_ma_grp.cu); arguments already validated by the caller
 int ma_grp_launch_step(const HwMaState *st, const void *actions, const HwMaOut *out, const MaConsts &C,

@@ -403,9 +403,14 @@ struct GrpStep {
     {
         const int S = A + 2;
         float2 *o2 = reinterpret_cast<float2 *>(ob);  // rows are 8-byte aligned: (4A+14)*4 bytes is a multiple of 8
-        o2[0] = make_float2(norm_f64(c.acc, -5.0, 5.0), norm_f64(c.steer, -30.0, 30.0));
-        o2[1] = make_float2(norm_f64(c.rx, 0.0, 1200.0), norm_f64(c.py, 0.0, 8.0));
-        o2[2 + S] = make_float2(norm_f64(c.vx, -20.0, 20.0), norm_f64(c.vy, -20.0, 20.0));
+        {   // the car itself; the normalisations go side by side in batches (ma_norm_n) so that their dependency chains overlap
+            const double raw[6] = {c.acc, c.steer, c.rx, c.py, c.vx, c.vy};
+            float o[6];
+            ma_norm_n<6, 0, 1, 2, 3, 6, 6>(raw, o);
+            o2[0] = make_float2(o[0], o[1]);
+            o2[1] = make_float2(o[2], o[3]);
+            o2[2 + S] = make_float2(o[4], o[5]);
+        }
         // other cars: car j goes to slot j - (j > a).  Walked by slot (j = s + (s >= a)) so that the lanes of a warp stay
         // converged: skipping "j == own index" inside a loop over j makes every lane skip a different iteration
 #pragma unroll
@@ -413,8 +418,11 @@ struct GrpStep {
             if (AT ? (sl >= AT - 1) : false) break;
             if (sl >= A - 1) break;
             const int j = sl + (sl >= g ? 1 : 0);
-            o2[2 + sl] = make_float2(norm_f64(dsub(pc[P_RX * CS + j], c.rx), -60.0, 60.0), norm_f64(dsub(pc[P_PY * CS + j], c.py), -8.0, 8.0));
-            o2[3 + S + sl] = make_float2(norm_f64(dsub(pc[(P_VX0 + cur) * CS + j], c.vx), -20.0, 20.0), norm_f64(dsub(pc[P_VY * CS + j], c.vy), -20.0, 20.0));
+            const double raw[4] = {dsub(pc[P_RX * CS + j], c.rx), dsub(pc[P_PY * CS + j], c.py), dsub(pc[(P_VX0 + cur) * CS + j], c.vx), dsub(pc[P_VY * CS + j], c.vy)};
+            float o[4];
+            ma_norm_n<4, 4, 5, 6, 6>(raw, o);
+            o2[2 + sl] = make_float2(o[0], o[1]);
+            o2[3 + S + sl] = make_float2(o[2], o[3]);
         }
         // per lane the obstacle nearest in raw x (first wins ties, insertion order): slot A-1+lane.  The slots of a lane are
         // picked out of the 2-bit lane fields of `olane`, so each slot is visited once, by its own lane's search.
@@ -433,8 +441,11 @@ struct GrpStep {
                 const bool take = d < nd;
                 dmov_if(take, nd, d); dmov_if(take, orx, krx); dmov_if(take, ovx, kvx);
             }
-            float2 pos = make_float2(norm_f64(dsub(orx, c.rx), -60.0, 60.0), norm_f64(dsub(lane_centre(l), c.py), -8.0, 8.0));
-            float2 vel = make_float2(norm_f64(dsub(ovx, c.vx), -20.0, 20.0), norm_f64(dsub(0.0, c.vy), -20.0, 20.0));
+            const double raw[4] = {dsub(orx, c.rx), dsub(lane_centre(l), c.py), dsub(ovx, c.vx), dsub(0.0, c.vy)};
+            float o[4];
+            ma_norm_n<4, 4, 5, 6, 6>(raw, o);
+            float2 pos = make_float2(o[0], o[1]);
+            float2 vel = make_float2(o[2], o[3]);
             if (!(nd < dinf())) {  // the reference raises here; flag it and emit the centre of the range
                 h.flags |= 2u;
                 pos = make_float2(0.5f, 0.5f); vel = make_float2(0.5f, 0.5f);

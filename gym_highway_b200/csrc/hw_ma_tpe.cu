@@ -16,8 +16,12 @@
 // observation rows so that they leave as contiguous 8-byte-per-lane streams (an environment's A rows of 4A+14 floats are
 // contiguous in the output, and so are the 32 environments of a warp).  State loads and stores are coalesced by
 // construction (structure of arrays, consecutive threads = consecutive environments).
-// Cost of the layout: ~165 registers per thread -> 12 warps per SM; the five independent cars of a thread give the
-// instruction-level parallelism that the lower occupancy takes away.
+// Cost of the layout: ~165 registers per thread -> 12 warps per SM (3 per scheduler), so the kernel lives on the instruction-level
+// parallelism inside a thread.  Measured on B200 (scripts/micro/fp64_latency.cu): DADD / DMUL / DFMA 8 cycles, DSETP -> its predicate
+// ~20, F2F / F2I / FRND ~18-21, LDS 29; a "compare -> conditional move -> compare" link therefore costs ~28 cycles, and ptxas
+// serialises independent chains when it is short of registers.  Hence: stages are written over all cars side by side (searches,
+// clamps on the original value, the 170 normalisations of the observation in batches), and rare work (spawn / retire, the exact
+// collision count behind an EXACT packed-rect filter) stays out of line.
 #include "hw_ma_common.cuh"
 
 namespace hw {
@@ -30,7 +34,7 @@ namespace hw {
 #endif
 constexpr int kTpeBlock = HW_TPE_BLOCK;
 #ifndef HW_TPE_SYNC
-#define HW_TPE_SYNC 1   // 1: block-synchronous ticks (282 us at 262 144 envs), 2: same loop without the barrier (299), 0: break out of the loop (307)
+#define HW_TPE_SYNC 1   // 1: block-synchronous ticks (252 us at 262 144 envs), 2: same loop without the barrier (301), 0: break out of the loop
 #endif
 #ifndef HW_TPE_SLOTS
 #define HW_TPE_SLOTS kMaxK
@@ -196,22 +200,31 @@ static __device__ HW_TPE_RARE_ATTR TpeSlots tpe_spawn_retire(TpeSlots h, double 
 }
 
 // exact check_collisions over the current obstacle list (fresh slots carry pygame's default rect) and the other cars: counters,
-// and the mask of the cars that collided.  Only reached when the tick's filter saw an overlap.
+// and the mask of the cars that collided.  Only reached when the tick's filter saw an overlap - with the exact filter that is a real
+// collision, once per episode - so it lives out of line (HW_TPE_COLLIDE_OOL): the cars' rects go in by value, the counts come back
+// packed in one word (hit mask | obstacle count << 8 | car count << 16), and the tick body is ~350 instructions shorter.
+#ifndef HW_TPE_COLLIDE_OOL
+#define HW_TPE_COLLIDE_OOL 1
+#endif
+template <int A> struct TpeRects { int ax75[A], ay37[A]; };
 template <int A>
-__device__ __forceinline__ uint32_t tpe_collide_exact(MaHead &h, const TpeCars<A> &c, const TpeOb ob)
+#if HW_TPE_COLLIDE_OOL
+static __device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+uint32_t tpe_collide_count(const TpeRects<A> r, const uint32_t nobs, const uint32_t ofresh, const uint32_t olane, const double *ob_base)
 {
-    int ax75[A], ay37[A];
-#pragma unroll
-    for (int a = 0; a < A; ++a) { ax75[a] = rect_x(c.px[a]) + 75; ay37[a] = rect_y(c.py[a]) + 37; }
+    const TpeOb ob{const_cast<double *>(ob_base)};
     uint32_t hit = 0;
     int no = 0, na = 0;
-    for (int k = 0; k < (int)h.nobs; ++k) {
-        const bool fresh = ((h.ofresh >> k) & 1u) != 0u;  // spawned in this tick: still pygame's default rect (0, 0, 76, 38)
+    for (int k = 0; k < (int)nobs; ++k) {
+        const bool fresh = ((ofresh >> k) & 1u) != 0u;  // spawned in this tick: still pygame's default rect (0, 0, 76, 38)
         const int bx = fresh ? 0 : rect_x(ob(k, O_PX));
-        const int by = fresh ? 0 : 80 * ob_lane(h, k) - 59;  // y = 21 + 80 * (lane - 1)
+        const int by = fresh ? 0 : 80 * (int)((olane >> (2 * k)) & 3u) - 59;  // y = 21 + 80 * (lane - 1)
 #pragma unroll
         for (int a = 0; a < A; ++a) {
-            const int o = tpe_overlap(ax75[a], ay37[a], bx, by);
+            const int o = tpe_overlap(r.ax75[a], r.ay37[a], bx, by);
             no += o; hit |= (uint32_t)o << a;
         }
     }
@@ -219,12 +232,22 @@ __device__ __forceinline__ uint32_t tpe_collide_exact(MaHead &h, const TpeCars<A
     for (int a = 0; a < A; ++a) {
 #pragma unroll
         for (int j = a + 1; j < A; ++j) {
-            const int o = tpe_overlap(ax75[a], ay37[a], ax75[j] - 75, ay37[j] - 37);
+            const int o = tpe_overlap(r.ax75[a], r.ay37[a], r.ax75[j] - 75, r.ay37[j] - 37);
             na += 2 * o; hit |= ((uint32_t)o << a) | ((uint32_t)o << j);
         }
     }
-    h.nc_obs += (uint32_t)no; h.nc_agent += (uint32_t)na;
-    return hit;
+    return hit | ((uint32_t)no << 8) | ((uint32_t)na << 16);  // at most 16 * 8 obstacle and 8 * 7 car overlaps
+}
+
+template <int A>
+__device__ __forceinline__ uint32_t tpe_collide_exact(MaHead &h, const TpeCars<A> &c, const TpeOb ob)
+{
+    TpeRects<A> r;
+#pragma unroll
+    for (int a = 0; a < A; ++a) { r.ax75[a] = rect_x(c.px[a]) + 75; r.ay37[a] = rect_y(c.py[a]) + 37; }
+    const uint32_t w = tpe_collide_count<A>(r, h.nobs, h.ofresh, h.olane, ob.base);
+    h.nc_obs += (w >> 8) & 0xFFu; h.nc_agent += w >> 16;
+    return w & 0xFFu;
 }
 
 // The per-tick overlap FILTER works on rects packed into one word, x in the upper and y in the lower 16 bits.  With
@@ -237,6 +260,10 @@ __device__ __forceinline__ uint32_t tpe_collide_exact(MaHead &h, const TpeCars<A
 // bits (and from the x field, which then fails or stays valid - the pair has failed already).  Fields cannot alias while
 // |dx| < 65 000 px, i.e. within 2 000 m: an episode moves a vehicle by 1 200 m at most.  min() over the masked words of all pairs
 // is zero iff some pair overlaps.
+#ifndef HW_TPE_OBS
+#define HW_TPE_OBS 0      // 1: obstacle update with an all-pairs search of the nearest car ahead instead of the running minimum - measured SLOWER
+                          // (268 vs 252 us: ten compare results at once do not fit the seven predicate registers and are shuffled through P2R / SEL)
+#endif
 #ifndef HW_TPE_FILTER2
 #define HW_TPE_FILTER2 1   // 0: the one-word (superset) filter
 #endif
@@ -478,6 +505,44 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
     for (int k = 0; k < (int)h.nobs; ++k) {
         const int lane = ob_lane(h, k);
         const double orx = ob(k, O_RX), iv = ob(k, O_IV);
+#if HW_TPE_OBS
+        // The nearest car ahead in the lane (first wins ties) WITHOUT a running minimum: a compare -> conditional move -> compare
+        // chain costs ~28 cycles per car on B200 (a DSETP delivers its predicate after ~20).  All candidate distances at once (inf for
+        // a car that is not ahead in this lane), all pairs compared side by side, the winner read off the predicates: car i wins iff
+        // it is valid and cand[i] <= cand[j] for every j > i and cand[j] > cand[i]... i.e. !(cand[j] <= cand[i]) for every j < i.
+        double cand[A];
+        bool w[A], any = false, sel = false;
+#pragma unroll
+        for (int j = 0; j < A; ++j) {
+            const double d = dsub(c.rx[j], orx);
+            w[j] = (c.ln[j] == lane) & (orx < c.rx[j]);
+            cand[j] = tpe_inf();
+            tmov_if(w[j], cand[j], d);
+            any = any | w[j];
+        }
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+#pragma unroll
+            for (int j = i + 1; j < A; ++j) {
+                const bool le = cand[i] <= cand[j];
+                w[i] = w[i] & le; w[j] = w[j] & !le;
+            }
+        }
+        // the winner's velocity: two short conditional-move chains over the halves of the cars, then one merge
+        constexpr int H = A / 2;
+        double bv = dcopy(c.vx[0]), bv2 = dcopy(c.vx[H]);
+        bool upper = w[H];
+#pragma unroll
+        for (int j = 1; j < H; ++j) tmov_if(w[j], bv, c.vx[j]);
+#pragma unroll
+        for (int j = H + 1; j < A; ++j) { tmov_if(w[j], bv2, c.vx[j]); upper = upper | w[j]; }
+        tmov_if(upper, bv, bv2);
+#pragma unroll
+        for (int j = 0; j < A; ++j) sel = sel | (w[j] & (c.vx[j] < iv));
+        double v = tclamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
+        tmov_if(any, v, iv);                 // else min(init_vx, that car's vx)
+        tmov_if(sel, v, bv);
+#else
         double bd = tpe_inf(), bv = iv;
 #pragma unroll
         for (int j = 0; j < A; ++j) {
@@ -488,6 +553,7 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         double v = tclamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
         tmov_if(bd < tpe_inf(), v, iv);        // else min(init_vx, that car's vx)
         tmov_if(bv < iv, v, bv);
+#endif
         const double odt = dmul(v, dt);
         const double opx = dsub(dadd(ob(k, O_PX), odt), lvdt);
         const double orx2 = dadd(orx, odt);
@@ -521,41 +587,6 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
     done |= hit;
     TPE_MARK(8);
     return hit;
-}
-
-// N normalisations (norm_f64: float32 cast, clip, (v - lo) / (hi - lo) in float64, float32 cast) evaluated stage by stage.  One value
-// is a chain of nine dependent instructions (~95 cycles with the three conversions); written one value after the other ptxas
-// emitted the 170 chains of a step back to back (a third of the kernel's stall samples sat in the epilogue).  Side by side the
-// N chains of a batch overlap.  BND: 0 = +-5, 1 = +-30, 2 = 0..1200, 3 = 0..8, 4 = +-60, 5 = +-8, 6 = +-20.
-#ifndef HW_TPE_EPI
-#define HW_TPE_EPI 1
-#endif
-__device__ __forceinline__ constexpr double tpe_bnd_lo(int b) { return b == 0 ? -5.0 : b == 1 ? -30.0 : b == 2 ? 0.0 : b == 3 ? 0.0 : b == 4 ? -60.0 : b == 5 ? -8.0 : -20.0; }
-__device__ __forceinline__ constexpr double tpe_bnd_hi(int b) { return b == 0 ? 5.0 : b == 1 ? 30.0 : b == 2 ? 1200.0 : b == 3 ? 8.0 : b == 4 ? 60.0 : b == 5 ? 8.0 : 20.0; }
-template <int N, int B0, int B1 = 0, int B2 = 0, int B3 = 0, int B4 = 0, int B5 = 0>
-__device__ __forceinline__ void tpe_norm_n(const double (&raw)[N], float (&out)[N])
-{
-    constexpr int B[6] = {B0, B1, B2, B3, B4, B5};
-    static_assert(N <= 6, "batch size");
-#if HW_TPE_EPI
-    float v[N];
-    double x[N], q0[N], e[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = (float)raw[i];
-#pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i], (float)tpe_bnd_lo(B[i])), (float)tpe_bnd_hi(B[i]));
-#pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = dsub((double)v[i], tpe_bnd_lo(B[i]));
-#pragma unroll
-    for (int i = 0; i < N; ++i) q0[i] = dmul(x[i], 1.0 / (tpe_bnd_hi(B[i]) - tpe_bnd_lo(B[i])));
-#pragma unroll
-    for (int i = 0; i < N; ++i) e[i] = __fma_rn(-q0[i], tpe_bnd_hi(B[i]) - tpe_bnd_lo(B[i]), x[i]);
-#pragma unroll
-    for (int i = 0; i < N; ++i) out[i] = (float)__fma_rn(e[i], 1.0 / (tpe_bnd_hi(B[i]) - tpe_bnd_lo(B[i])), q0[i]);
-#else
-#pragma unroll
-    for (int i = 0; i < N; ++i) out[i] = norm_f64(raw[i], tpe_bnd_lo(B[i]), tpe_bnd_hi(B[i]));
-#endif
 }
 
 // MultiAgentEnv._get_obs_norm (highway_env.py:139-149) of one value: see norm_f64
@@ -592,13 +623,13 @@ __device__ __forceinline__ uint32_t tpe_observe_obstacles(MaHead &h, const TpeCa
             if (a0 + 1 < A) {
                 const double raw[4] = {dsub(brx[a0], c.rx[a0]), dsub(bvx[a0], c.vx[a0]), dsub(brx[a0 + 1], c.rx[a0 + 1]), dsub(bvx[a0 + 1], c.vx[a0 + 1])};
                 float o[4];
-                tpe_norm_n<4, 4, 6, 4, 6>(raw, o);
+                ma_norm_n<4, 4, 6, 4, 6>(raw, o);
                 odx[a0][l] = none ? 0.5f : o[0]; odv[a0][l] = none ? 0.5f : o[1];
                 odx[a0 + 1][l] = none ? 0.5f : o[2]; odv[a0 + 1][l] = none ? 0.5f : o[3];
             } else {
                 const double raw[2] = {dsub(brx[a0], c.rx[a0]), dsub(bvx[a0], c.vx[a0])};
                 float o[2];
-                tpe_norm_n<2, 4, 6>(raw, o);
+                ma_norm_n<2, 4, 6>(raw, o);
                 odx[a0][l] = none ? 0.5f : o[0]; odv[a0][l] = none ? 0.5f : o[1];
             }
         }
@@ -615,7 +646,7 @@ __device__ __forceinline__ void tpe_observe_row(const TpeCars<A> &c, const int a
     {   // the car itself: acc, steer, raw x, y, vx, vy
         const double raw[6] = {c.acc[a], c.steer[a], c.rx[a], c.py[a], c.vx[a], c.vy[a]};
         float o[6];
-        tpe_norm_n<6, 0, 1, 2, 3, 6, 6>(raw, o);
+        ma_norm_n<6, 0, 1, 2, 3, 6, 6>(raw, o);
         put(0, make_float2(o[0], o[1]));
         put(1, make_float2(o[2], o[3]));
         put(2 + S, make_float2(o[4], o[5]));
@@ -626,14 +657,14 @@ __device__ __forceinline__ void tpe_observe_row(const TpeCars<A> &c, const int a
         const int sl = j - (j > a ? 1 : 0);
         const double raw[4] = {dsub(c.rx[j], c.rx[a]), dsub(c.py[j], c.py[a]), dsub(c.vx[j], c.vx[a]), dsub(c.vy[j], c.vy[a])};
         float o[4];
-        tpe_norm_n<4, 4, 5, 6, 6>(raw, o);
+        ma_norm_n<4, 4, 5, 6, 6>(raw, o);
         put(2 + sl, make_float2(o[0], o[1]));
         put(3 + S + sl, make_float2(o[2], o[3]));
     }
     {   // obstacles: slot A - 1 + lane; the lateral offsets to the three lane centres and the (common) relative lateral velocity
         const double raw[4] = {dsub(lane_centre(0), c.py[a]), dsub(lane_centre(1), c.py[a]), dsub(lane_centre(2), c.py[a]), dsub(0.0, c.vy[a])};
         float o[4];
-        tpe_norm_n<4, 5, 5, 5, 6>(raw, o);
+        ma_norm_n<4, 5, 5, 5, 6>(raw, o);
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             const int s = A - 1 + l;

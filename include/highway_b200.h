@@ -49,7 +49,7 @@ extern "C" {
                                        * (a third / two thirds of that for three / four cars, always for one or two: fewer instructions
                                        * per environment), the lane-per-car kernel below (five times the threads for the smallest
                                        * batches).  Same results either way. */
-#define HW_MA_TPE_MIN_ENVS 24576
+#define HW_MA_TPE_MIN_ENVS 16384
 
 /* discrete actions, gym_highway/envs/highway_env.py:14-20 */
 #define HW_ACT_LEFT 0
