@@ -267,6 +267,59 @@ def side_measure(kind, continuous, n, dev, rank, args, steps=100, warmup=5, agen
     return out
 
 
+def stream_measure(kind, continuous, n, dev, rank, agents=5, rounds=4, replays=5):
+    """A small batch the way a rollout issues it: launches back to back (one CUDA graph, no host in between), so launch latency
+    overlaps the previous kernel.  L2 rule: the graph round-robins over enough independent batches of `n` envs that the combined
+    working set is over twice the L2 - every launch finds its batch evicted ("inputs larger than L2", no flush kernel in the timed
+    region).  Time = CUDA events around the graph replays / number of launches."""
+    import torch
+    info = dict(kind=kind, continuous=continuous)
+    a = argparse.Namespace(agents=agents)
+    bps = SA_BYTES_PER_STEP[continuous] if kind == "sa" else ma_bytes_per_step(agents, 16)
+    batches = max(2, int(np.ceil(2.2 * L2_BYTES / (n * bps))))
+    envs, A = [], 1
+    for b in range(batches):
+        if kind == "sa":
+            from gym_highway_b200 import HighwayVecEnv
+            e = HighwayVecEnv(n, continuous=continuous, seed=0, device=dev, env_id0=(rank * batches + b) * n)
+        else:
+            from gym_highway_b200 import HighwayMAVecEnv
+            e = HighwayMAVecEnv(n, num_agents=agents, continuous=continuous, seed=0, device=dev, env_id0=(rank * batches + b) * n)
+            A = agents
+        envs.append(e)
+    acts = make_actions(info, n, A, dev, rank, ring=rounds)
+    for e in envs:  # decorrelate the batches: episodes at different phases
+        if hasattr(e, "rollout_random"):
+            e.rollout_random(150, action_ctr0=0)
+        for w in range(40 if kind == "ma" else 3):
+            e.step_async(acts[w % rounds]); e.step_wait()
+    torch.cuda.synchronize(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g):
+            for r in range(rounds):
+                for e in envs:
+                    e.step_async(acts[r]); e.step_wait()
+        g.replay()  # warm-up replay
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(side)
+        for _ in range(replays):
+            g.replay()
+        t1.record(side)
+    torch.cuda.synchronize(dev)
+    launches = replays * rounds * batches
+    t = t0.elapsed_time(t1) * 1e-3 / launches
+    out = {"envs": n, "batches": batches, "launches_timed": launches, "us_per_launch_back_to_back": t * 1e6, "env_steps_per_s": n / t,
+           "achieved_GBps": n * bps / t / 1e9, "roofline_frac": n * bps / t / 1e9 / measured_peak()[0],
+           "l2": "%d independent batches of %d envs stepped round-robin from one CUDA graph: %.0f MB combined working set vs %d MB L2, no flush "
+                 "kernel" % (batches, n, batches * n * bps / 1e6, L2_BYTES // 1000000)}
+    del envs, acts, g
+    torch.cuda.empty_cache()
+    return out
+
+
 def rollout_measure(dev, rank, world, envs=131072, nsteps=240, rollouts=3):
     """BASELINE.json configs[3]: ppo2 rollout collection (policy forward + sampling + env step + GAE), DeviceRunner under one
     CUDA graph per rollout; every rank collects from its own `envs` environments, statistics all-reduced once per rollout"""
@@ -433,14 +486,16 @@ def main():
     if not args.no_extras and world == 1 and info["kind"] == "sa" and not info["continuous"] and n != 65536:
         # configs[1]: 65,536 single-agent envs on one GPU (0.43 waves: latency-bound), L2 flushed between launches
         c1 = side_measure("sa", False, 65536, dev, rank, args, steps=200, warmup=10)
-        extras["configs1"] = dict(c1, workload="configs[1]: 65,536 single-agent envs on 1 GPU, discrete random actions")
+        extras["configs1"] = dict(c1, workload="configs[1]: 65,536 single-agent envs on 1 GPU, discrete random actions",
+                                  back_to_back=stream_measure("sa", False, 65536, dev, rank))
         extras["sa_16m"] = dict(side_measure("sa", False, 16777216, dev, rank, args, steps=30, warmup=3),
                                 workload="configs[4]: the 16,777,216-env point (largest single-GPU configuration), discrete")
         extras["continuous"] = dict(side_measure("sa", True, 4194304, dev, rank, args, steps=60, warmup=5),
                                     workload="single-agent continuous actions (HighwayEnvContinuous), 4,194,304 envs")
         extras["configs2"] = {
             "workload": "configs[2]: multi-agent env, 5 cars (+3..16 obstacles) per env, uniform random discrete actions, car-car collisions",
-            "envs_16384": side_measure("ma", False, 16384, dev, rank, args, steps=200, warmup=10),
+            "envs_16384": dict(side_measure("ma", False, 16384, dev, rank, args, steps=200, warmup=10),
+                               back_to_back=stream_measure("ma", False, 16384, dev, rank)),
             "envs_262144": side_measure("ma", False, 262144, dev, rank, args, steps=60, warmup=5),
             "continuous_262144": side_measure("ma", True, 262144, dev, rank, args, steps=60, warmup=5)}
     if not args.no_extras and info["kind"] == "sa" and not info["continuous"]:

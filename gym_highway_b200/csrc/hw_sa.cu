@@ -86,9 +86,11 @@ __device__ __noinline__ int sa_collide_exact(double px, double py, double o0, do
 template <bool CONT>
 __device__ __forceinline__ double road_clamp(double y)
 {
-    // `if y < lo: y = lo  elif y > 6: y = min(y, 7)`: for lo <= y <= 6 the min is the identity
-    dset_if(7.0 < y, y, 7.0);
-    dset_if(y < (CONT ? 1.0 : 0.0), y, CONT ? 1.0 : 0.0);
+    // `if y < lo: y = lo  elif y > 6: y = min(y, 7)`: for lo <= y <= 6 the min is the identity.  Both tests read the value before
+    // either move (they exclude each other), so the two DSETP issue back to back (a DSETP delivers its predicate after ~20 cycles)
+    const bool over = 7.0 < y, under = y < (CONT ? 1.0 : 0.0);
+    dset_if(over, y, 7.0);
+    dset_if(under, y, CONT ? 1.0 : 0.0);
     return y;
 }
 
@@ -372,8 +374,14 @@ __device__ __forceinline__ void sa_tick_later(SaEnv &e, int &lane, int &ncol, in
     }
     {
         double v = dadd(e.vx, dmul(e.acc, dt));
+#if HW_CLAMP_PAR
+        const bool over = 20.0 < v, under = !(v > 0.0);  // max(0.0, v) is v only when v > 0; both tests on the value before either move
+        dset_if(over, v, 20.0);
+        dset_if(under, v, 0.0);
+#else
         dset_if(20.0 < v, v, 20.0);
         dset_if(!(v > 0.0), v, 0.0);  // max(0.0, v) is v only when v > 0
+#endif
         e.vx = v;
     }
     const double vdt = dmul(e.vx, dt);
