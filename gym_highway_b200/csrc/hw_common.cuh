@@ -130,8 +130,9 @@ __device__ __forceinline__ double lane_centre(int k)  // k = lane-1: 1.25, 3.75,
 }
 
 // pygame Rect stores ints; assigning a float truncates toward zero
-__device__ __forceinline__ int rect_x(double px) { return __double2int_rz(dsub(dmul(px, 32.0), 38.0)); }
-__device__ __forceinline__ int rect_y(double py) { return __double2int_rz(dsub(dmul(py, 32.0), 19.0)); }
+// (x * 32 is exact - a power of two - so the product and the subtraction round once, and one FMA returns the same bits)
+__device__ __forceinline__ int rect_x(double px) { return __double2int_rz(__fma_rn(px, 32.0, -38.0)); }
+__device__ __forceinline__ int rect_y(double py) { return __double2int_rz(__fma_rn(py, 32.0, -19.0)); }
 
 __device__ __forceinline__ bool rects_overlap(int ax, int ay, int bx, int by)
 {
