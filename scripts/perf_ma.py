@@ -5,7 +5,8 @@ import torch
 from gym_highway_b200 import HighwayMAVecEnv
 
 def probe(n, A=5, cont=False, steps=40, kernel=os.environ.get('HW_MA_KERNEL', 'auto')):
-    env = HighwayMAVecEnv(n, num_agents=A, continuous=cont, seed=0, kernel=kernel, exact_steering=bool(int(os.environ.get('HW_EXACT', '0'))))
+    env = HighwayMAVecEnv(n, num_agents=A, continuous=cont, seed=0, kernel=kernel, exact_steering=bool(int(os.environ.get('HW_EXACT', '0'))),
+                          num_slots=int(os.environ.get('HW_MA_SLOTS', '16')))
     g = torch.Generator(device='cuda'); g.manual_seed(1)
     acts = (torch.rand((8, n, A, 2), generator=g, device='cuda') * 2 - 1) if cont else torch.randint(0, 4, (8, n, A), generator=g, device='cuda', dtype=torch.int32)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
