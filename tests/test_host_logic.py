@@ -317,3 +317,26 @@ def test_ring_memory_matches_sequential_appends():
     rms.update(x[:20]); rms.update(x[20:])
     assert torch.allclose(rms.mean.double(), x.mean(0), atol=1e-6)
     assert torch.allclose(rms.std.double(), x.std(0, unbiased=False).clamp(min=0.1), atol=1e-6)
+
+
+def test_packed_rect_filter_of_the_thread_per_env_kernel_is_exact():
+    """The per-tick collision filter of csrc/hw_ma_tpe.cu (tpe_filter_word) restated in uint32 arithmetic: the masked word is zero iff
+    the two 76 x 38 rects overlap (pygame.Rect.colliderect, highway_core.py:401-422) - for every offset around the boundaries and for
+    rect coordinates on either side of zero (the packing wraps modulo 2^16 per field)."""
+    MASK, BIAS, SIZE = np.uint32(0xFF00FF80), np.uint32((105 << 16) + 53), np.uint32((75 << 16) + 37)
+
+    def pack(x, y):
+        return ((x.astype(np.int64) << 16) + y.astype(np.int64)).astype(np.uint32)
+
+    dx, dy = np.meshgrid(np.arange(-400, 401), np.arange(-200, 201), indexing="ij")
+    with np.errstate(over="ignore"):
+        for bx0, by0 in ((282, 101), (-1318, 21), (0, 0), (3162, 181), (-30, -19), (40000, 101), (-20000, 21)):
+            bx, by = np.full_like(dx, bx0), np.full_like(dy, by0)
+            ax, ay = bx + dx, by + dy
+            pa, pb = pack(ax + 75, ay + 37), pack(bx, by)
+            word = ((pa - pb + BIAS) | (pb - pa + (np.uint32(2) * SIZE + BIAS))) & MASK
+            overlap = (ax < bx + 76) & (ay < by + 38) & (ax + 76 > bx) & (ay + 38 > by)
+            assert np.array_equal(word == 0, overlap), (bx0, by0)
+            # the one-word filter of round 2a is a superset only: it also passes a rect up to 180 px ahead
+            one = (pa - pb + BIAS) & MASK
+            assert np.all((one == 0) | ~overlap) and np.any((one == 0) & ~overlap)
