@@ -474,6 +474,26 @@ def main():
            "api": ("HighwayVecEnv.step_host -> hw_sa_step_host" if info["kind"] == "sa" else "HighwayMAVecEnv.step_host -> hw_ma_step_host")
                   + " (C ABI, host buffers: pinned-host actions H2D, kernel, obs/rew/done D2H, stream drain, all inside the call)",
            "host_binding": numa_note}
+    if info["kind"] == "sa":
+        # the same call with HW_FLAG_COMPACT_OBS: observation rows of 14 floats (the four constant columns stay on the device side of PCIe)
+        for w in range(2):
+            env.step_host(h_acts[w % ring], compact=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            env.step_host(h_acts[k % ring], compact=True)
+        torch.cuda.synchronize(dev)
+        t_c = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([t_c], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_c = float(t.item())
+        e2e["compact_obs"] = {"value": world * n * e2e_steps / t_c, "unit": "env-steps/s", "ms_per_step": 1e3 * t_c / e2e_steps,
+                              "d2h_bytes_per_step": n * (14 * 4 + 4 + 1),
+                              "note": "step_host(compact=True): [N, 14] observation rows, columns 11/13/15/17 (constant 0.5) dropped; "
+                                      "HighwayVecEnv.expand_obs restores the reference layout on the host; not the headline e2e"}
     stats = env.episode_statistics()
     live = None
     if info["kind"] == "ma":

@@ -18,11 +18,14 @@ FLAG_SHARED_REWARD = 16
 FLAG_EXACT_STEERING = 32
 FLAG_MA_THREAD_PER_ENV = 64
 FLAG_MA_LANE_PER_CAR = 128
+FLAG_COMPACT_OBS = 256
 MA_MAX_AGENTS = 5
 MA_MAX_AGENTS_EXT = 8
 MA_MAX_SLOTS = 16
 
 SA_OBS_DIM = 18
+SA_OBS_DIM_COMPACT = 14
+SA_COMPACT_COLUMNS = (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16)  # the four dropped columns (11, 13, 15, 17) are the constant 0.5
 
 
 class HwSimParams(C.Structure):

@@ -451,40 +451,60 @@ struct PtrRow {
 // and every obstacle velocity is its init_vx (5..7, DESIGN.md deviation 5) or the car's vx, so np.clip is the identity on
 // py, the three lane offsets, vx and the three relative velocities - 16 compare-selects per step the kernel does not issue.
 // acc (<= 5 + dt), steer (<= 30 + 30*dt), raw x (<= 1220) and the obstacle distances (spawns 70..100 ahead) do clip.
-template <bool STEPPED, class Row>
+// COMPACT (HW_FLAG_COMPACT_OBS): rows of 14 floats - columns 11, 13, 15, 17 (the lateral velocities, always zero -> the constant 0.5) are
+// dropped, i.e. the row is the first ten columns followed by {vx, dv0, dv1, dv2}.
+template <bool STEPPED, class Row, bool COMPACT = false>
 __device__ __forceinline__ void sa_observe(const SaEnv &e, const Row row)
 {
     constexpr bool C = !STEPPED;
     row.put(0, make_float2(norm_f32(e.acc, -5.f, 5.f), norm_f32(e.steer, -30.f, 30.f)));
     row.put(1, make_float2(norm_f32<true>(e.rx, 0.f, 1200.f), norm_f32<false, C>(e.py, 0.f, 8.f)));
+    float dv[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         row.put(2 + k, make_float2(norm_f32(dsub(e.orx[k], e.rx), -60.f, 60.f),
                                    norm_f32<false, C>(dsub(lane_centre(k), e.py), -8.f, 8.f)));
-        row.put(6 + k, make_float2(norm_f32<false, C>(dsub(e.ovx[k], e.vx), -20.f, 20.f), 0.5f));
+        dv[k] = norm_f32<false, C>(dsub(e.ovx[k], e.vx), -20.f, 20.f);
     }
-    row.put(5, make_float2(norm_f32<false, C>(e.vx, -20.f, 20.f), 0.5f));
+    const float vxn = norm_f32<false, C>(e.vx, -20.f, 20.f);
+    if (COMPACT) {
+        row.put(5, make_float2(vxn, dv[0]));
+        row.put(6, make_float2(dv[1], dv[2]));
+    } else {
+        row.put(5, make_float2(vxn, 0.5f));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) row.put(6 + k, make_float2(dv[k], 0.5f));
+    }
 }
 
 // Observation + state store of an environment that has just been stepped (no reset), without materialising ovx[] in
 // fp64: the velocity an obstacle had after its last update is its init_vx, except for the one that is being held back
 // behind the car (`slow`, in the car's lane), which moved with the car's vx - its relative velocity is exactly 0 -> 0.5.
+template <bool COMPACT>
 __device__ __forceinline__ void sa_finish_stepped(const SaEnv &e, const SmRow row, const SaPtrs &S, uint32_t i)
 {
     const int held = e.slow ? (int)((e.bits >> HW_BITS_LANE_SHIFT) & 3u) : 0;
     const float vxf = (float)e.vx, pyf = (float)e.py, rxf = (float)e.rx, accf = (float)e.acc, steerf = (float)e.steer;
     row.put(0, make_float2(norm_f32(e.acc, -5.f, 5.f), norm_f32(e.steer, -30.f, 30.f)));
     row.put(1, make_float2(norm_f32<true>(e.rx, 0.f, 1200.f), norm_f32<false, false>(e.py, 0.f, 8.f)));
-    row.put(5, make_float2(norm_f32<false, false>(e.vx, -20.f, 20.f), 0.5f));
-    float ovf[3], oif[3];
+    const float vxn = norm_f32<false, false>(e.vx, -20.f, 20.f);
+    float ovf[3], oif[3], dvn[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         row.put(2 + k, make_float2(norm_f32(dsub(e.orx[k], e.rx), -60.f, 60.f),
                                    norm_f32<false, false>(dsub(lane_centre(k), e.py), -8.f, 8.f)));
         const float dv = norm_f32<false, false>(dsub(e.oiv[k], e.vx), -20.f, 20.f);
-        row.put(6 + k, make_float2(held == k + 1 ? 0.5f : dv, 0.5f));
+        dvn[k] = held == k + 1 ? 0.5f : dv;
         oif[k] = (float)e.oiv[k];
         ovf[k] = held == k + 1 ? vxf : oif[k];
+    }
+    if (COMPACT) {
+        row.put(5, make_float2(vxn, dvn[0]));
+        row.put(6, make_float2(dvn[1], dvn[2]));
+    } else {
+        row.put(5, make_float2(vxn, 0.5f));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) row.put(6 + k, make_float2(dvn[k], 0.5f));
     }
     S.car_a[i] = make_float4((float)e.px, pyf, rxf, vxf);
     S.car_b[i] = make_float4(accf, steerf, (float)e.cruise, __uint_as_float(e.bits));
@@ -504,20 +524,22 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
     return v;
 }
 
-// tile_s: shared-state-space address of the warp's tile
+// tile_s: shared-state-space address of the warp's tile; D = floats per row (18, or 14 with HW_FLAG_COMPACT_OBS: 32 x 56 bytes = 112 stores)
+template <int D = HW_SA_OBS_DIM>
 __device__ __forceinline__ void store_obs_warp(const uint32_t tile_s, float *__restrict__ obs, int64_t warp_base, int64_t n)
 {
     __syncwarp();
     const uint32_t lane = threadIdx.x & 31;
     const int64_t rows = min((int64_t)32, n - warp_base);
-    float *dst = obs + warp_base * HW_SA_OBS_DIM;
+    float *dst = obs + warp_base * D;
     if (rows == 32) {
         float4 *d4 = reinterpret_cast<float4 *>(dst);
+        constexpr int kVec = 32 * D / 4, kFull = kVec / 32, kRem = kVec % 32;  // 144 = 4 x 32 + 16, 112 = 3 x 32 + 16
 #pragma unroll
-        for (int v = 0; v < 4; ++v) d4[lane + 32 * v] = lds128(tile_s + 16u * (lane + 32 * v));
-        if (lane < 16) d4[lane + 128] = lds128(tile_s + 16u * (lane + 128));
+        for (int v = 0; v < kFull; ++v) d4[lane + 32 * v] = lds128(tile_s + 16u * (lane + 32 * v));
+        if (kRem && lane < kRem) d4[lane + 32 * kFull] = lds128(tile_s + 16u * (lane + 32 * kFull));
     } else {
-        for (uint32_t f = lane; f < (uint32_t)rows * HW_SA_OBS_DIM; f += 32) {
+        for (uint32_t f = lane; f < (uint32_t)rows * D; f += 32) {
             float v;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(tile_s + 4u * f) : "memory");
             dst[f] = v;
@@ -536,7 +558,7 @@ __device__ __forceinline__ void store_obs_warp(const uint32_t tile_s, float *__r
 #define HW_SA_MIN_BLOCKS_C (2048 / HW_SA_BLOCK / 2)
 #endif
 
-template <bool CONT, bool RANDOM_ACTIONS, bool EXACT>
+template <bool CONT, bool RANDOM_ACTIONS, bool EXACT, bool COMPACT = false>
 __global__ void __launch_bounds__(kSaBlock, CONT ? HW_SA_MIN_BLOCKS_C : HW_SA_MIN_BLOCKS_D)
 sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ obs, float *__restrict__ rew,
                uint8_t *__restrict__ done, int4 *__restrict__ term, unsigned long long *__restrict__ stats,
@@ -544,11 +566,12 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                const int steps_arg, const int64_t n, const int flags)
 {
     const int steps = RANDOM_ACTIONS ? steps_arg : 1;  // step() proper is one step per launch: lets the episode bookkeeping fold
+    constexpr int D = COMPACT ? HW_SA_OBS_DIM_COMPACT : HW_SA_OBS_DIM;  // floats per observation row
 
-    __shared__ __align__(16) float sm_obs[kSaBlock * HW_SA_OBS_DIM];
+    __shared__ __align__(16) float sm_obs[kSaBlock * D];
     const uint32_t i = blockIdx.x * kSaBlock + threadIdx.x;  // < 2^31, checked by the launcher
     const int64_t warp_base = (int64_t)(i - (threadIdx.x & 31));
-    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(sm_obs) + (threadIdx.x >> 5) * (32 * HW_SA_OBS_DIM * 4);
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(sm_obs) + (threadIdx.x >> 5) * (32 * D * 4);
     if (warp_base >= n) return;  // whole warp out of range
     const bool inf_obs = !(flags & HW_FLAG_NO_INF_OBS);
     const bool autoreset = !(flags & HW_FLAG_NO_AUTORESET);
@@ -632,7 +655,7 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                 // `e = start grid` ahead of a common store, ptxas spilled the whole 19-double state around the branch.)
                 rew[i] = (float)milli_to_reward(rew_milli, reward);
                 done[i] = is_done ? 1 : 0;
-                const SmRow row{tile_s + (threadIdx.x & 31) * (HW_SA_OBS_DIM * 4)};
+                const SmRow row{tile_s + (threadIdx.x & 31) * (D * 4)};
                 uint4 st = S.stat[i];  // per-env counters: read-modify-write once per launch
                 st.x += ncoll_step; st.y = e.spawn_ctr; st.z = (uint32_t)((int)st.z + rew_milli); st.w += 1;
                 if (is_done) {  // Monitor / info of the finished episode
@@ -643,14 +666,14 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
                     SaEnv r;
                     sa_reset_env(r);
                     r.spawn_ctr = 0;
-                    sa_observe<false>(r, row);
+                    sa_observe<false, SmRow, COMPACT>(r, row);
                     sa_store(r, S, i);
                     st.x = 0; st.z = 0; st.w = 0;
                 } else {
                     // gym per-env semantics (no auto-reset) stepped far past the time-out: the 16-bit tick field saturates
                     // instead of carrying into the lane bits (the episode has been over for 60000 ticks; only `done` matters)
                     if (tick >= 0xFF00u) e.bits = (e.bits & ~HW_BITS_TICK_MASK) | 0xFF00u;
-                    sa_finish_stepped(e, row, S, i);
+                    sa_finish_stepped<COMPACT>(e, row, S, i);
                 }
                 S.stat[i] = st;
             } else {
@@ -677,7 +700,7 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
         if (RANDOM_ACTIONS) {
             rew[i] = (float)milli_to_reward(rew_milli, reward);
             done[i] = is_done ? 1 : 0;
-            sa_observe<true>(e, SmRow{tile_s + (threadIdx.x & 31) * (HW_SA_OBS_DIM * 4)});
+            sa_observe<true, SmRow, COMPACT>(e, SmRow{tile_s + (threadIdx.x & 31) * (D * 4)});
             sa_store(e, S, i);
             {   // per-env counters: read-modify-write once per launch
                 uint4 st = S.stat[i];
@@ -687,7 +710,7 @@ sa_step_kernel(SaPtrs S, const void *__restrict__ actions, float *__restrict__ o
             }
         }
     }
-    store_obs_warp(tile_s, obs, warp_base, n);
+    store_obs_warp<D>(tile_s, obs, warp_base, n);
     if (stats && __any_sync(0xffffffffu, acc_eps != 0)) {  // all 32 lanes are here (warps entirely out of range returned at the top)
         {
             const long long eps = warp_sum(acc_eps);
@@ -770,10 +793,13 @@ static int launch_step_range(const HwSaState *st, const void *actions, const HwS
     if (i0 < 0 || count < 1 || i0 + count > n || (i0 & 1)) return HW_E_BADARG;  // an even i0 keeps the observation rows 16-byte aligned
     const bool cont = (flags & HW_FLAG_CONTINUOUS) != 0;
     const bool exact = (flags & HW_FLAG_EXACT_STEERING) != 0;
+    const bool compact = (flags & HW_FLAG_COMPACT_OBS) != 0;
+    if (compact && random_actions) return HW_E_BADARG;  // the compact rows are an option of step() / step_host() only
+    const int obs_dim = compact ? HW_SA_OBS_DIM_COMPACT : HW_SA_OBS_DIM;
     if (count >= ((int64_t)1 << 31)) return HW_E_BADARG;  // environments of one launch are indexed with 32 bits
     const SaPtrs S = ptrs(st, n, i0);
     const void *act = actions ? static_cast<const char *>(actions) + (size_t)i0 * (cont ? 2 * sizeof(float) : sizeof(int32_t)) : nullptr;
-    float *obs = out->obs + i0 * HW_SA_OBS_DIM, *rew = out->rew + i0;
+    float *obs = out->obs + i0 * obs_dim, *rew = out->rew + i0;
     uint8_t *done = out->done + i0;
     int4 *term = out->term ? reinterpret_cast<int4 *>(out->term) + i0 : nullptr;
     SaConsts K;
@@ -786,10 +812,11 @@ static int launch_step_range(const HwSaState *st, const void *actions, const HwS
     K.ticks_per_step = P->ticks_per_step;
     K.timeout_tick = P->timeout_tick;
     const unsigned grid = (unsigned)((count + kSaBlock - 1) / kSaBlock);
-#define HW_LAUNCH(C, R, E) sa_step_kernel<C, R, E><<<grid, kSaBlock, 0, stream>>>(S, act, obs, rew, done, term, out->stats, K, seed, env_id0 + (uint64_t)i0, action_ctr0, steps, count, flags)
-#define HW_LAUNCH_E(C, R) do { if (exact) HW_LAUNCH(C, R, true); else HW_LAUNCH(C, R, false); } while (0)
-    if (cont) { if (random_actions) HW_LAUNCH_E(true, true); else HW_LAUNCH_E(true, false); }
-    else      { if (random_actions) HW_LAUNCH_E(false, true); else HW_LAUNCH_E(false, false); }
+#define HW_LAUNCH(C, R, E, P) sa_step_kernel<C, R, E, P><<<grid, kSaBlock, 0, stream>>>(S, act, obs, rew, done, term, out->stats, K, seed, env_id0 + (uint64_t)i0, action_ctr0, steps, count, flags)
+#define HW_LAUNCH_E(C, R, P) do { if (exact) HW_LAUNCH(C, R, true, P); else HW_LAUNCH(C, R, false, P); } while (0)
+    if (compact)   { if (cont) HW_LAUNCH_E(true, false, true); else HW_LAUNCH_E(false, false, true); }
+    else if (cont) { if (random_actions) HW_LAUNCH_E(true, true, false); else HW_LAUNCH_E(true, false, false); }
+    else           { if (random_actions) HW_LAUNCH_E(false, true, false); else HW_LAUNCH_E(false, false, false); }
 #undef HW_LAUNCH_E
 #undef HW_LAUNCH
     return (int)cudaGetLastError();
@@ -867,6 +894,7 @@ int hw_sa_step_host(const HwSaState *state, const void *h_actions, void *d_actio
     // upload and the kernel of the second half run under the download of the first.
     // (Measured on B200 / PCIe Gen5 at 4 M envs: 6.87 ms unsplit, 6.73 ms in two halves, worse again from eight chunks on:
     // the download alone is 6.3 ms at the link's ~51 GB/s, so there is little left to hide.)
+    const int obs_dim = (flags & HW_FLAG_COMPACT_OBS) ? HW_SA_OBS_DIM_COMPACT : HW_SA_OBS_DIM;
     const int chunks = (n >= 262144 && s2 != nullptr && s2 != s) ? 2 : 1;
     const int64_t per = (((n + chunks - 1) / chunks) + 127) & ~(int64_t)127;
     cudaEvent_t ev = nullptr;
@@ -885,7 +913,7 @@ int hw_sa_step_host(const HwSaState *state, const void *h_actions, void *d_actio
         if (ce != cudaSuccess) { rc = (int)ce; break; }
         rc = hw::launch_step_range(state, d_actions, d_out, params, seed, env_id0, 0, 1, false, n, i0, cnt, flags, q);
         if (rc) break;
-        ce = cudaMemcpyAsync(h_obs + i0 * HW_SA_OBS_DIM, d_out->obs + i0 * HW_SA_OBS_DIM, (size_t)cnt * HW_SA_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, q);
+        ce = cudaMemcpyAsync(h_obs + i0 * obs_dim, d_out->obs + i0 * obs_dim, (size_t)cnt * obs_dim * sizeof(float), cudaMemcpyDeviceToHost, q);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_rew + i0, d_out->rew + i0, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, q);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_done + i0, d_out->done + i0, (size_t)cnt, cudaMemcpyDeviceToHost, q);
         if (ce != cudaSuccess) rc = (int)ce;

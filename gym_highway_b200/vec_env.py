@@ -309,9 +309,13 @@ class HighwayVecEnv(VecEnv):
         out = self._out[self._cur]
         return self._wrap(out['obs']), self._wrap(out['rew']), self._wrap(out['done'], True)
 
-    def step_host(self, actions):
+    def step_host(self, actions, compact=False):
         """Host-buffer step through hw_sa_step_host: numpy actions in, numpy (obs, rew, done) out, with the
-        host<->device copies and the stream drain inside the call."""
+        host<->device copies and the stream drain inside the call.
+
+        `compact=True` (HW_FLAG_COMPACT_OBS): the observation comes back as [N, 14] - the four columns that are the constant 0.5
+        (11, 13, 15, 17: the lateral velocities, always zero in this simulator) never cross PCIe, which is what bounds this call;
+        `expand_obs` restores the reference's [N, 18] layout on the host when a consumer wants it."""
         n = self.num_envs
         if self._host is None:
             self._host = dict(
@@ -327,13 +331,27 @@ class HighwayVecEnv(VecEnv):
         h['act'].copy_(torch.as_tensor(np.asarray(actions)).reshape(h['act'].shape))
         self._cur ^= 1
         self._serial += 1
+        # compact rows reuse the same device and host buffers: [N, 14] is a prefix of their storage
+        out = self._out_c[self._cur]
+        h_obs = h['obs'].view(-1)[:n * _lib.SA_OBS_DIM_COMPACT].view(n, _lib.SA_OBS_DIM_COMPACT) if compact else h['obs']
         with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_step_host"):
             rc = self._lib.hw_sa_step_host(C.byref(self._state_c), _as_ptr(h['act']), _as_ptr(h['d_act']),
-                                           C.byref(self._out_c[self._cur]), _as_ptr(h['obs']), _as_ptr(h['rew']),
+                                           C.byref(out), _as_ptr(h_obs), _as_ptr(h['rew']),
                                            _as_ptr(h['done']), C.byref(self.params), self._seed, self._env_id0,
-                                           n, self._flags, self._stream(), C.c_void_p(h['aux'].cuda_stream))
+                                           n, self._flags | (_lib.FLAG_COMPACT_OBS if compact else 0), self._stream(),
+                                           C.c_void_p(h['aux'].cuda_stream))
         _lib.check(rc, "hw_sa_step_host")
-        return h['obs'].numpy(), h['rew'].numpy(), h['done'].numpy().view(np.bool_)  # the kernel writes 0 / 1
+        return h_obs.numpy(), h['rew'].numpy(), h['done'].numpy().view(np.bool_)  # the kernel writes 0 / 1
+
+    @staticmethod
+    def expand_obs(compact_obs, out=None):
+        """[N, 14] compact observation rows -> the reference's [N, 18] layout (columns 11, 13, 15, 17 = 0.5)"""
+        c = np.asarray(compact_obs)
+        if out is None:
+            out = np.empty((c.shape[0], _lib.SA_OBS_DIM), np.float32)
+        out[:, 11:18:2] = 0.5
+        out[:, list(_lib.SA_COMPACT_COLUMNS)] = c
+        return out
 
     # ------------------------------------------------------------------ infos / statistics
     def _make_info_fetcher(self, out):

@@ -50,6 +50,11 @@ extern "C" {
                                        * per environment), the lane-per-car kernel below (five times the threads for the smallest
                                        * batches).  Same results either way. */
 #define HW_MA_TPE_MIN_ENVS 16384
+#define HW_FLAG_COMPACT_OBS 256  /* single-agent hw_sa_step / hw_sa_step_host: observation rows of HW_SA_OBS_DIM_COMPACT = 14 floats instead of 18 -
+                                  * columns 11, 13, 15, 17 (the lateral velocities of the car and the three obstacles: always zero, i.e. the
+                                  * constant 0.5 after normalisation, multi_lane_sim.py:1062-1090) are dropped: row = columns 0..9, then
+                                  * {10, 12, 14, 16}.  22 % fewer bytes over PCIe for a host consumer; HighwayVecEnv.expand_obs() restores
+                                  * the reference layout.  `obs` buffers are then [n][14]. */
 
 /* discrete actions, gym_highway/envs/highway_env.py:14-20 */
 #define HW_ACT_LEFT 0
@@ -58,6 +63,7 @@ extern "C" {
 #define HW_ACT_MAINTAIN 3
 
 #define HW_SA_OBS_DIM 18
+#define HW_SA_OBS_DIM_COMPACT 14
 #define HW_MA_MAX_AGENTS 5   /* the reference's start grid holds five cars (simple_base.py:32-38) */
 #define HW_MA_MAX_AGENTS_EXT 8 /* EXTENSION beyond the reference (no reference parity, the CPU restatement is its only
                                 * specification): 6..8 cars on a start grid that continues the reference's staggered rows

@@ -70,3 +70,28 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.HighwayLibraryError):
         _lib.load()
+
+
+def test_binding_constants_mirror_the_header():
+    """every HW_FLAG_* / dimension the Python binding uses has the header's value"""
+    from gym_highway_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "highway_b200.h")).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define\s+(HW_[A-Z0-9_]+)\s+(\(?-?[0-9xXa-fA-F]+\)?)\s", text)
+            if re.fullmatch(r"-?(0[xX][0-9a-fA-F]+|\d+)", m.group(2))}
+    for py, c in (("FLAG_CONTINUOUS", "HW_FLAG_CONTINUOUS"), ("FLAG_NO_INF_OBS", "HW_FLAG_NO_INF_OBS"), ("FLAG_NO_AUTORESET", "HW_FLAG_NO_AUTORESET"),
+                  ("FLAG_SHARED_REWARD", "HW_FLAG_SHARED_REWARD"), ("FLAG_EXACT_STEERING", "HW_FLAG_EXACT_STEERING"),
+                  ("FLAG_MA_THREAD_PER_ENV", "HW_FLAG_MA_THREAD_PER_ENV"), ("FLAG_MA_LANE_PER_CAR", "HW_FLAG_MA_LANE_PER_CAR"),
+                  ("FLAG_COMPACT_OBS", "HW_FLAG_COMPACT_OBS"), ("SA_OBS_DIM", "HW_SA_OBS_DIM"), ("SA_OBS_DIM_COMPACT", "HW_SA_OBS_DIM_COMPACT"),
+                  ("ABI_VERSION", "HW_ABI_VERSION")):
+        assert getattr(_lib, py) == defs[c], (py, c)
+    assert len(_lib.SA_COMPACT_COLUMNS) == _lib.SA_OBS_DIM_COMPACT
+    assert sorted(set(range(_lib.SA_OBS_DIM)) - set(_lib.SA_COMPACT_COLUMNS)) == [11, 13, 15, 17]
+
+
+def test_expand_obs_restores_the_reference_layout():
+    import numpy as np
+    from gym_highway_b200 import _lib
+    from gym_highway_b200.vec_env import HighwayVecEnv
+    full = np.random.RandomState(0).rand(9, _lib.SA_OBS_DIM).astype(np.float32)
+    full[:, 11:18:2] = 0.5
+    assert np.array_equal(HighwayVecEnv.expand_obs(full[:, list(_lib.SA_COMPACT_COLUMNS)]), full)

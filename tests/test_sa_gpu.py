@@ -211,6 +211,32 @@ def test_host_buffer_step_matches_device_step(n, steps, continuous):
         assert torch.equal(sa[k], sb[k]), k
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,continuous", [(4096 + 37, False), (300001, False), (4096 + 37, True)])
+def test_compact_observation_rows_are_the_reference_rows_without_the_constant_columns(n, continuous):
+    """HW_FLAG_COMPACT_OBS: [N, 14] rows = the reference's 18 columns minus 11, 13, 15, 17, which are 0.5 in every row (auto-reset rows
+    included); everything else the step produces is unchanged, and expand_obs() restores the reference layout bit for bit."""
+    from gym_highway_b200 import _lib
+    a, b = _env(n, seed=3, continuous=continuous), _env(n, seed=3, continuous=continuous)
+    rng = np.random.RandomState(1)
+    a.rollout_random(60); b.rollout_random(60)
+    keep = list(_lib.SA_COMPACT_COLUMNS)
+    ndone = 0
+    for t in range(12):
+        act = rng.uniform(-1, 1, (n, 2)).astype(np.float32) if continuous else rng.randint(0, 4, n).astype(np.int32)
+        o1, r1, d1 = a.step_host(act)
+        o2, r2, d2 = b.step_host(act, compact=True)
+        assert o2.shape == (n, _lib.SA_OBS_DIM_COMPACT)
+        assert np.all(o1[:, 11:18:2] == 0.5)
+        assert bits_equal(o1[:, keep], o2) and bits_equal(r1, r2) and np.array_equal(d1, d2)
+        assert bits_equal(type(b).expand_obs(o2), o1)
+        ndone += int(d1.sum())
+    assert ndone > 0  # rows written by the auto-reset path were compared too
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+
+
 def test_rollout_random_is_deterministic_and_sane():
     a, b = _env(2048, seed=4), _env(2048, seed=4)
     oa, ra, da = a.rollout_random(37, action_ctr0=5)
