@@ -135,6 +135,34 @@ def load():
     return lib
 
 
+def launch_ctx(device_index, name):
+    """context of one library call: the CUDA device of the environment made current (only when it is not - the usual case costs a
+    comparison instead of torch.cuda.device's enter / exit) and, with HW_NVTX=1, an NVTX range around the launch"""
+    import torch
+    if torch.cuda.current_device() != device_index:
+        return _LaunchCtx(device_index, name)
+    return nvtx_range(name)
+
+
+class _LaunchCtx(object):
+    def __init__(self, device_index, name):
+        import torch
+        self._dev, self._rng = torch.cuda.device(device_index), nvtx_range(name)
+
+    def __enter__(self):
+        self._dev.__enter__(); self._rng.__enter__()
+
+    def __exit__(self, *exc):
+        self._rng.__exit__(*exc); self._dev.__exit__(*exc)
+        return False
+
+
+def raw_stream(device_index):
+    """cudaStream_t of torch's current stream on `device_index` as an int (the C call torch.cuda.current_stream() wraps: no Stream object)"""
+    import torch
+    return torch._C._cuda_getCurrentRawStream(device_index)
+
+
 def check(rc, what):
     if rc != 0:
         msg = load().hw_error_string(rc)

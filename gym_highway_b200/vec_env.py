@@ -153,6 +153,7 @@ class HighwayVecEnv(VecEnv):
         if not torch.cuda.is_available():
             raise _lib.HighwayLibraryError("HighwayVecEnv needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.continuous = bool(continuous)
         self.real_time = bool(real_time)
         self.params = _lib.sim_params(real_time)
@@ -195,7 +196,7 @@ class HighwayVecEnv(VecEnv):
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(_lib.raw_stream(self._dev_index))
 
     def seed(self, seed=None):
         """env i draws its respawn uniforms from Philox keyed by (seed, env_id0 + i) — the batched
@@ -216,7 +217,7 @@ class HighwayVecEnv(VecEnv):
             if n == 1 and arr.shape != shape and arr.size == (2 if self.continuous else 1):
                 arr = arr.reshape(shape)
             a = torch.from_numpy(np.ascontiguousarray(arr, np.float32 if self.continuous else np.int64))
-        if a.numel() != int(np.prod(shape)):
+        if a.numel() != n * (2 if self.continuous else 1):
             raise AssertionError("actions {} is either not a list or has a wrong size - cannot match to {} "
                                  "environments".format(tuple(a.shape), n))
         a = a.reshape(shape)
@@ -228,7 +229,7 @@ class HighwayVecEnv(VecEnv):
         if self.return_numpy:
             a = t.cpu().numpy()
             return a.astype(bool) if as_bool else a
-        return t.bool() if as_bool else t
+        return t.view(torch.bool) if as_bool else t  # the kernels write 0 / 1 bytes: a view, not a conversion launch per step
 
     # ------------------------------------------------------------------ VecEnv API
     def reset(self):
@@ -237,7 +238,7 @@ class HighwayVecEnv(VecEnv):
         self._pending = None
         self._serial += 1
         out = self._out[self._cur]
-        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_reset"):
+        with _lib.launch_ctx(self._dev_index, "hw_sa_reset"):
             rc = self._lib.hw_sa_reset(C.byref(self._state_c), None, _as_ptr(out['obs']), self.num_envs, self._stream())
         _lib.check(rc, "hw_sa_reset")
         return self._wrap(out['obs'])
@@ -246,7 +247,7 @@ class HighwayVecEnv(VecEnv):
         """reset the environments whose mask entry is non-zero (only needed with auto_reset=False)"""
         mask = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
         assert mask.numel() == self.num_envs
-        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_reset"):
+        with _lib.launch_ctx(self._dev_index, "hw_sa_reset"):
             rc = self._lib.hw_sa_reset(C.byref(self._state_c), _as_ptr(mask), None, self.num_envs, self._stream())
         _lib.check(rc, "hw_sa_reset")
         return self.observe()
@@ -266,7 +267,7 @@ class HighwayVecEnv(VecEnv):
         a = self._coerce_actions(actions)
         self._cur ^= 1
         self._serial += 1
-        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_step"):
+        with _lib.launch_ctx(self._dev_index, "hw_sa_step"):
             rc = self._lib.hw_sa_step(C.byref(self._state_c), _as_ptr(a), C.byref(self._out_c[self._cur]),
                                       C.byref(self.params), self._seed, self._env_id0, self.num_envs, self._flags,
                                       self._stream())
@@ -291,7 +292,7 @@ class HighwayVecEnv(VecEnv):
         self._serial += 1
         out = _lib.HwSaOut(obs.data_ptr(), rew.data_ptr(), done.data_ptr(), self._out[0]['term'].data_ptr(),
                            self.stats.data_ptr() if self.stats is not None else 0)
-        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_step"):
+        with _lib.launch_ctx(self._dev_index, "hw_sa_step"):
             rc = self._lib.hw_sa_step(C.byref(self._state_c), _as_ptr(actions), C.byref(out), C.byref(self.params),
                                       self._seed, self._env_id0, self.num_envs, self._flags, self._stream())
         _lib.check(rc, "hw_sa_step")
@@ -301,7 +302,7 @@ class HighwayVecEnv(VecEnv):
         returns the last step's (obs, rew, done)"""
         self._cur ^= 1
         self._serial += 1
-        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_rollout_random"):
+        with _lib.launch_ctx(self._dev_index, "hw_sa_rollout_random"):
             rc = self._lib.hw_sa_rollout_random(C.byref(self._state_c), C.byref(self._out_c[self._cur]),
                                                 C.byref(self.params), self._seed, self._env_id0, int(action_ctr0),
                                                 int(steps), self.num_envs, self._flags, self._stream())
@@ -334,7 +335,7 @@ class HighwayVecEnv(VecEnv):
         # compact rows reuse the same device and host buffers: [N, 14] is a prefix of their storage
         out = self._out_c[self._cur]
         h_obs = h['obs'].view(-1)[:n * _lib.SA_OBS_DIM_COMPACT].view(n, _lib.SA_OBS_DIM_COMPACT) if compact else h['obs']
-        with torch.cuda.device(self.device), _lib.nvtx_range("hw_sa_step_host"):
+        with _lib.launch_ctx(self._dev_index, "hw_sa_step_host"):
             rc = self._lib.hw_sa_step_host(C.byref(self._state_c), _as_ptr(h['act']), _as_ptr(h['d_act']),
                                            C.byref(out), _as_ptr(h_obs), _as_ptr(h['rew']),
                                            _as_ptr(h['done']), C.byref(self.params), self._seed, self._env_id0,

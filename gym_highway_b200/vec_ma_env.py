@@ -48,6 +48,7 @@ class HighwayMAVecEnv(VecEnv):
         if not torch.cuda.is_available():
             raise _lib.HighwayLibraryError("HighwayMAVecEnv needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.n = self.num_agents = int(num_agents)
         self.num_slots = int(num_slots)
         self.continuous = bool(continuous)
@@ -94,7 +95,7 @@ class HighwayMAVecEnv(VecEnv):
         self.reset()
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(_lib.raw_stream(self._dev_index))
 
     def seed(self, seed=None):
         if seed is not None:
@@ -120,14 +121,14 @@ class HighwayMAVecEnv(VecEnv):
         if self.return_numpy:
             x = t.cpu().numpy()
             return x.astype(bool) if as_bool else x
-        return t.bool() if as_bool else t
+        return t.view(torch.bool) if as_bool else t  # the kernels write 0 / 1 bytes: a view, not a conversion launch per step
 
     def reset(self):
         assert not self.closed
         self._pending = None
         self._serial += 1
         out = self._out[self._cur]
-        with torch.cuda.device(self.device), _lib.nvtx_range("hw_ma_reset"):
+        with _lib.launch_ctx(self._dev_index, "hw_ma_reset"):
             rc = self._lib.hw_ma_reset(C.byref(self._state_c), None, _as_ptr(out['obs']), self.num_envs, self._stream())
         _lib.check(rc, "hw_ma_reset")
         return self._wrap(out['obs'])
@@ -146,7 +147,7 @@ class HighwayMAVecEnv(VecEnv):
         a = self._coerce_actions(actions)
         self._cur ^= 1
         self._serial += 1
-        with torch.cuda.device(self.device), _lib.nvtx_range("hw_ma_step"):
+        with _lib.launch_ctx(self._dev_index, "hw_ma_step"):
             rc = self._lib.hw_ma_step(C.byref(self._state_c), _as_ptr(a), C.byref(self._out_c[self._cur]),
                                       C.byref(self.params), self._seed, self._env_id0, self.num_envs, self._flags,
                                       self._stream())
@@ -171,7 +172,7 @@ class HighwayMAVecEnv(VecEnv):
         self._serial += 1
         out = _lib.HwMaOut(obs.data_ptr(), rew.data_ptr(), done.data_ptr(), self._out[0]['term'].data_ptr(),
                            self.stats.data_ptr() if self.stats is not None else 0)
-        with torch.cuda.device(self.device), _lib.nvtx_range("hw_ma_step"):
+        with _lib.launch_ctx(self._dev_index, "hw_ma_step"):
             rc = self._lib.hw_ma_step(C.byref(self._state_c), _as_ptr(actions), C.byref(out), C.byref(self.params),
                                       self._seed, self._env_id0, self.num_envs, self._flags, self._stream())
         _lib.check(rc, "hw_ma_step")
@@ -189,7 +190,7 @@ class HighwayMAVecEnv(VecEnv):
         h['act'].copy_(torch.as_tensor(np.asarray(actions)).reshape(h['act'].shape))
         self._cur ^= 1
         self._serial += 1
-        with torch.cuda.device(self.device), _lib.nvtx_range("hw_ma_step_host"):
+        with _lib.launch_ctx(self._dev_index, "hw_ma_step_host"):
             rc = self._lib.hw_ma_step_host(C.byref(self._state_c), _as_ptr(h['act']), _as_ptr(h['d_act']),
                                            C.byref(self._out_c[self._cur]), _as_ptr(h['obs']), _as_ptr(h['rew']),
                                            _as_ptr(h['done']), C.byref(self.params), self._seed, self._env_id0,
