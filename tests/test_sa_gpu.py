@@ -353,3 +353,21 @@ def test_full_size_properties_4m_envs():
     assert st["episodes"] > n and st["timeouts"] > 0 and st["obs_collisions"] >= st["episodes"] - st["timeouts"]
     assert 1.0 <= st["mean_length"] <= 240.0
 
+
+
+def test_env_on_another_device_than_the_current_one():
+    """the launch context switches to the environment's device only when it is not current: an env on cuda:1 stepped while cuda:0 is
+    current gives what the same env gives on cuda:0 (needs two GPUs)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    assert torch.cuda.current_device() == 0
+    n = 2048 + 5
+    a, b = _env(n, seed=6), _env(n, seed=6, device="cuda:1")
+    rng = np.random.RandomState(3)
+    for t in range(30):
+        act = rng.randint(0, 4, n).astype(np.int32)
+        o1, r1, d1, _ = a.step(torch.from_numpy(act).cuda())
+        o2, r2, d2, _ = b.step(torch.from_numpy(act).to("cuda:1"))
+        assert o2.device.index == 1 and torch.cuda.current_device() == 0
+        assert bits_equal(o1.cpu().numpy(), o2.cpu().numpy()) and bits_equal(r1.cpu().numpy(), r2.cpu().numpy())
+        assert np.array_equal(d1.cpu().numpy(), d2.cpu().numpy())
