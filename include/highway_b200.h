@@ -107,7 +107,7 @@ typedef struct HwSaState {
  * [2] sum of episode returns in milli-reward (two's complement), [3] sum of obstacle collisions,
  * [4] episodes ended by time-out, [5..7] reserved. */
 typedef struct HwSaOut {
-    float *obs;      /* [n][18], post-reset observation where done */
+    float *obs;      /* [n][18] ([n][14] with HW_FLAG_COMPACT_OBS), post-reset observation where done */
     float *rew;      /* [n] */
     uint8_t *done;   /* [n] */
     int32_t *term;   /* [n][4], nullable */
@@ -141,7 +141,8 @@ int hw_sa_rollout_random(const HwSaState *state, const HwSaOut *out, const HwSim
  * after the copies have landed.  When `aux_stream` is a second (caller-owned, long-lived) stream, batches of
  * 262,144 environments and more run as two half-batch launches, the second one on `aux_stream`, so that its upload
  * and kernel overlap the first half's download; with aux_stream NULL the call is one upload, one launch, one download.
- * d_actions and d_out are caller-owned DEVICE staging buffers of the same shapes; h_* should be page-locked
+ * d_actions and d_out are caller-owned DEVICE staging buffers of the same shapes (h_obs and d_out->obs are [n][14] with
+ * HW_FLAG_COMPACT_OBS); h_* should be page-locked
  * (and allocated on the GPU's NUMA node) for full copy bandwidth. */
 int hw_sa_step_host(const HwSaState *state, const void *h_actions, void *d_actions, const HwSaOut *d_out,
                     float *h_obs, float *h_rew, uint8_t *h_done, const HwSimParams *params,
