@@ -38,20 +38,6 @@ __device__ __forceinline__ double ddiv_const(double x, const double c)
 // against 36 % for the fp64 pipe).
 //   dmov_if: if (p) x = y for y in a register: ONE predicated DMUL by 1.0 (exact for every y, -0.0 included).
 //   dset_if: if (p) x = c for a literal c: predicated moves (a single CS2R / DMUL for zero).
-#ifndef HW_DSEL
-#define HW_DSEL 0   // 1: selp.f64 (two 32-bit selects) instead of a predicated DMUL.  Measured: no gain for a latency-bound 65 536-env launch
-                    // (15.3 vs 15.2 us), slower when issue-bound (295 vs 281 us at 4 M envs)
-#endif
-#if HW_DSEL
-__device__ __forceinline__ void dmov_if(bool p, double &x, double y)
-{
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\tselp.f64 %0, %2, %0, q;\n\t}" : "+d"(x) : "r"((int)p), "d"(y));
-}
-__device__ __forceinline__ void dmov_if_nz(uint32_t w, double &x, double y)
-{
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\tselp.f64 %0, %2, %0, q;\n\t}" : "+d"(x) : "r"(w), "d"(y));
-}
-#else
 __device__ __forceinline__ void dmov_if(bool p, double &x, double y)
 {
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmul.rn.f64 %0, %2, 0d3FF0000000000000;\nHW_SKIP:\n\t}" : "+d"(x) : "r"((int)p), "d"(y));
@@ -63,7 +49,6 @@ __device__ __forceinline__ void dmov_if_nz(uint32_t w, double &x, double y)
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmul.rn.f64 %0, %2, 0d3FF0000000000000;\nHW_SKIP:\n\t}" : "+d"(x) : "r"(w), "d"(y));
 }
 
-#endif
 
 // a copy that costs ONE instruction (DMUL by 1.0) instead of the two 32-bit moves of a plain assignment; for values that
 // seed a chain of dmov_if's
@@ -98,29 +83,20 @@ __device__ __forceinline__ void dsel3x2(int sel, double a0, double a1, double a2
 
 __device__ __forceinline__ void dset_if(bool p, double &x, double c)
 {
-#if HW_DSEL
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\tselp.f64 %0, %2, %0, q;\n\t}" : "+d"(x) : "r"((int)p), "d"(c));
-    return;
-#endif
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@!q bra HW_SKIP;\n\tmov.f64 %0, %2;\nHW_SKIP:\n\t}" : "+d"(x) : "r"((int)p), "d"(c));
 }
 
 // python max(lo, min(x, hi)): min keeps x unless hi < x; max keeps lo unless the inner value is > lo.  (Spelled with
 // conditional moves: NVVM turns the C++ ternary `(x > lo) ? x : lo` into max.f64, whose NaN-aware expansion on sm_100a is
 // six instructions.)
-#ifndef HW_CLAMP_PAR
-#define HW_CLAMP_PAR 1   // 1: both tests on the original x (they exclude each other), so the two DSETP issue back to back
-#endif
+// Both tests read the ORIGINAL x (x > hi implies x > lo, so the second test cannot fire after the first moved x to hi; a NaN fails
+// the first and passes the second either way): the two DSETP issue back to back instead of the second one waiting for the first
+// conditional move - a DSETP delivers its predicate after ~20 cycles on B200 (scripts/micro/fp64_latency.cu).
 __device__ __forceinline__ double py_clamp(double x, const double lo, const double hi)
 {
-#if HW_CLAMP_PAR
     const bool over = hi < x, under = !(x > lo);
     dset_if(over, x, hi);
     dset_if(under, x, lo);
-#else
-    dset_if(hi < x, x, hi);
-    dset_if(!(x > lo), x, lo);
-#endif
     return x;
 }
 

@@ -91,9 +91,6 @@ __device__ __forceinline__ float norm_f64(double raw, const double lo, const dou
 // is a chain of nine dependent instructions (~95 cycles with the three conversions); written one value after the other ptxas
 // emitted the 170 chains of a step back to back (a third of the kernel's stall samples sat in the epilogue).  Side by side the
 // N chains of a batch overlap.  BND: 0 = +-5, 1 = +-30, 2 = 0..1200, 3 = 0..8, 4 = +-60, 5 = +-8, 6 = +-20.
-#ifndef HW_MA_NORM_BATCH
-#define HW_MA_NORM_BATCH 1
-#endif
 __device__ __forceinline__ constexpr double ma_bnd_lo(int b) { return b == 0 ? -5.0 : b == 1 ? -30.0 : b == 2 ? 0.0 : b == 3 ? 0.0 : b == 4 ? -60.0 : b == 5 ? -8.0 : -20.0; }
 __device__ __forceinline__ constexpr double ma_bnd_hi(int b) { return b == 0 ? 5.0 : b == 1 ? 30.0 : b == 2 ? 1200.0 : b == 3 ? 8.0 : b == 4 ? 60.0 : b == 5 ? 8.0 : 20.0; }
 template <int N, int B0, int B1 = 0, int B2 = 0, int B3 = 0, int B4 = 0, int B5 = 0>
@@ -101,7 +98,6 @@ __device__ __forceinline__ void ma_norm_n(const double (&raw)[N], float (&out)[N
 {
     constexpr int B[6] = {B0, B1, B2, B3, B4, B5};
     static_assert(N <= 6, "batch size");
-#if HW_MA_NORM_BATCH
     float v[N];
     double x[N], q0[N], e[N];
 #pragma unroll
@@ -116,10 +112,6 @@ __device__ __forceinline__ void ma_norm_n(const double (&raw)[N], float (&out)[N
     for (int i = 0; i < N; ++i) e[i] = __fma_rn(-q0[i], ma_bnd_hi(B[i]) - ma_bnd_lo(B[i]), x[i]);
 #pragma unroll
     for (int i = 0; i < N; ++i) out[i] = (float)__fma_rn(e[i], 1.0 / (ma_bnd_hi(B[i]) - ma_bnd_lo(B[i])), q0[i]);
-#else
-#pragma unroll
-    for (int i = 0; i < N; ++i) out[i] = norm_f64(raw[i], ma_bnd_lo(B[i]), ma_bnd_hi(B[i]));
-#endif
 }
 
 

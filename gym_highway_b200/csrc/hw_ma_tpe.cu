@@ -41,65 +41,12 @@ constexpr int kTpeBlock = HW_TPE_BLOCK;
 #endif
 constexpr int kTpeWarpDoubles = HW_TPE_SLOTS * O_NF * 32;  // one warp's obstacle region: 16 KB for 16 slots
 
-// Conditional moves of doubles.  HW_TPE_FSEL = 0: the shared helpers (one predicated DMUL / predicated moves: fewest issue slots,
-// but the move sits on the fp64 pipe with its latency); 1: selp.f64, i.e. a pair of 32-bit selects on the ALU pipe (one more
-// instruction, a third of the latency) - this kernel is bound by dependent-instruction latency, not by issue slots.
-#ifndef HW_TPE_FSEL
-#define HW_TPE_FSEL 0
-#endif
-#if HW_TPE_FSEL
-__device__ __forceinline__ void tmov_if(bool p, double &x, double y)
-{
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\tselp.f64 %0, %2, %0, q;\n\t}" : "+d"(x) : "r"((int)p), "d"(y));
-}
-__device__ __forceinline__ void tmov_if_nz(uint32_t w, double &x, double y)
-{
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\tselp.f64 %0, %2, %0, q;\n\t}" : "+d"(x) : "r"(w), "d"(y));
-}
-__device__ __forceinline__ void tset_if(bool p, double &x, double c) { tmov_if(p, x, c); }
-__device__ __forceinline__ double tclamp(double x, const double lo, const double hi)
-{
-    const bool over = hi < x, under = !(x > lo);
-    tset_if(over, x, hi);
-    tset_if(under, x, lo);
-    return x;
-}
-#else
+// Conditional moves of doubles: the shared helpers (one predicated DMUL / predicated moves).  selp.f64 - a pair of 32-bit selects on
+// the ALU pipe - measured slower here as well (268 vs 252 us, profiles/r4_variants.md).
 __device__ __forceinline__ void tmov_if(bool p, double &x, double y) { dmov_if(p, x, y); }
 __device__ __forceinline__ void tmov_if_nz(uint32_t w, double &x, double y) { dmov_if_nz(w, x, y); }
 __device__ __forceinline__ void tset_if(bool p, double &x, double c) { dset_if(p, x, c); }
-#ifndef HW_TPE_CLAMP
-#define HW_TPE_CLAMP 1
-#endif
-// python max(lo, min(x, hi)).  Both tests read the ORIGINAL x (x > hi implies x > lo, so the second test cannot fire after the first
-// moved x to hi; a NaN fails the first and passes the second either way): the two DSETP issue back to back instead of the second
-// one waiting for the first conditional move - a DSETP takes ~20 cycles to deliver its predicate on B200, a dependent pair ~57.
-__device__ __forceinline__ double tclamp(double x, const double lo, const double hi)
-{
-#if HW_TPE_CLAMP
-    const bool over = hi < x, under = !(x > lo);
-    dset_if(over, x, hi);
-    dset_if(under, x, lo);
-    return x;
-#else
-    return py_clamp(x, lo, hi);
-#endif
-}
-#endif
-
-// HW_TPE_PROF (experiment builds only): per-phase clock64() accounting of the step, summed over the warps into g_tpe_prof and read
-// back through hw_debug_tpe_prof (scripts/tpe_phase_profile.py).  Off: the macros vanish.
-#ifdef HW_TPE_PROF
-__device__ unsigned long long g_tpe_prof[16];
-struct TpeProf { long long t[12]; long long last; };
-#define TPE_PROF_ARG , TpeProf &prof
-#define TPE_PROF_PASS , prof
-#define TPE_MARK(k) do { const long long now_ = clock64(); prof.t[k] += now_ - prof.last; prof.last = now_; } while (0)
-#else
-#define TPE_PROF_ARG
-#define TPE_PROF_PASS
-#define TPE_MARK(k) do { } while (0)
-#endif
+__device__ __forceinline__ double tclamp(double x, const double lo, const double hi) { return py_clamp(x, lo, hi); }
 
 struct TpeOb {  // this thread's column of the warp-private obstacle region
     double *base;
@@ -203,16 +150,9 @@ static __device__ HW_TPE_RARE_ATTR TpeSlots tpe_spawn_retire(TpeSlots h, double 
 // and the mask of the cars that collided.  Only reached when the tick's filter saw an overlap - with the exact filter that is a real
 // collision, once per episode - so it lives out of line (HW_TPE_COLLIDE_OOL): the cars' rects go in by value, the counts come back
 // packed in one word (hit mask | obstacle count << 8 | car count << 16), and the tick body is ~350 instructions shorter.
-#ifndef HW_TPE_COLLIDE_OOL
-#define HW_TPE_COLLIDE_OOL 1
-#endif
 template <int A> struct TpeRects { int ax75[A], ay37[A]; };
 template <int A>
-#if HW_TPE_COLLIDE_OOL
 static __device__ __noinline__
-#else
-__device__ __forceinline__
-#endif
 uint32_t tpe_collide_count(const TpeRects<A> r, const uint32_t nobs, const uint32_t ofresh, const uint32_t olane, const double *ob_base)
 {
     const TpeOb ob{const_cast<double *>(ob_base)};
@@ -260,24 +200,13 @@ __device__ __forceinline__ uint32_t tpe_collide_exact(MaHead &h, const TpeCars<A
 // bits (and from the x field, which then fails or stays valid - the pair has failed already).  Fields cannot alias while
 // |dx| < 65 000 px, i.e. within 2 000 m: an episode moves a vehicle by 1 200 m at most.  min() over the masked words of all pairs
 // is zero iff some pair overlaps.
-#ifndef HW_TPE_OBS
-#define HW_TPE_OBS 0      // 1: obstacle update with an all-pairs search of the nearest car ahead instead of the running minimum - measured SLOWER
-                          // (268 vs 252 us: ten compare results at once do not fit the seven predicate registers and are shuffled through P2R / SEL)
-#endif
-#ifndef HW_TPE_FILTER2
-#define HW_TPE_FILTER2 1   // 0: the one-word (superset) filter
-#endif
 constexpr uint32_t kRectMask = 0xFF00FF80u;
 constexpr uint32_t kRectBias = (105u << 16) + 53u;
 constexpr uint32_t kRectSize = (75u << 16) + 37u;
 // pa = pack(ax + 75, ay + 37) of a car, pb = pack(bx, by) of the other rect: the masked test word
 __device__ __forceinline__ uint32_t tpe_filter_word(uint32_t pa, uint32_t pb)
 {
-#if HW_TPE_FILTER2
     return ((pa - pb + kRectBias) | (pb - pa + (2u * kRectSize + kRectBias))) & kRectMask;
-#else
-    return (pa - pb + kRectBias) & kRectMask;
-#endif
 }
 __device__ __forceinline__ uint32_t tpe_pack_rect(int x, int y) { return ((uint32_t)x << 16) + (uint32_t)y; }
 
@@ -285,18 +214,13 @@ __device__ __forceinline__ uint32_t tpe_pack_rect(int x, int y) { return ((uint3
 template <int A, bool CONT, bool EXACT>
 __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const TpeOb ob, const int K, const MaConsts &C, const double dt,
                                              const bool inf_obs, const uint32_t (&amask)[A], const double (&a0)[A], const double (&a1)[A],
-                                             const uint64_t seed, const uint64_t env_id, uint32_t &done TPE_PROF_ARG)
+                                             const uint64_t seed, const uint64_t env_id, uint32_t &done)
 {
-    TPE_MARK(1);
     h.tick += 1;
     if (h.tick >= (uint32_t)C.timeout_tick) done |= (1u << A) - 1u;  // highway_core.py:276-277
 
     // ---- actions for every car in id order (highway_core.py:280-281, :110-188): maintain() of car a sees the lanes the cars
     //      before it have just switched to and the old lanes of the cars after it - program order ----
-#ifndef HW_TPE_ACT
-#define HW_TPE_ACT 1
-#endif
-#if HW_TPE_ACT
     if (CONT) {
 #pragma unroll
         for (int a = 0; a < A; ++a) {
@@ -355,51 +279,6 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
             for (int a = 0; a < A; ++a) tmov_if_nz(fire[a] & kBitDoMaint, c.cruise[a], bvx[a]);
         }
     }
-#else
-    const uint32_t live = live_mask(h.nobs);
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-        if (CONT) {
-            c.acc[a] = tclamp(dadd(c.acc[a], a0[a]), -5.0, 5.0);
-            c.steer[a] = tclamp(dadd(c.steer[a], a1[a]), -30.0, 30.0);
-            continue;
-        }
-        // amask = the mode bit the action asks for; it fires when not yet set.  The two modes of a pair exclude each other, so
-        // setting the bit and clearing its partner is the identity when nothing fires.
-        const uint32_t am = amask[a];
-        const uint32_t apair = am | ((am & (kBitLeft | kBitDoAcc)) << 1) | ((am & (kBitRight | kBitDoMaint)) >> 1);
-        const uint32_t fire = am & ~c.b[a];
-        c.b[a] = (c.b[a] & ~apair) | am;
-        if (fire & kBitDoMaint) {
-            // all_obstacles iterates the cars (id order) and then the obstacles (insertion order): nearest strictly ahead in the lane,
-            // first wins ties
-            const int lane = c.ln[a];
-            double bpx = tpe_inf(), bvx = c.vx[a];
-#pragma unroll
-            for (int j = 0; j < A; ++j) {
-                if (j == a) continue;
-                const bool take = (c.ln[j] == lane) & (c.px[j] > c.px[a]) & (c.px[j] < bpx);
-                tmov_if(take, bpx, c.px[j]); tmov_if(take, bvx, c.vx[j]);
-            }
-            const uint32_t diff = h.olane ^ ((uint32_t)lane * 0x55555555u);
-            uint32_t same = ~(diff | (diff >> 1)) & 0x55555555u & live;
-            while (same) {
-                const int k = (__ffs((int)same) - 1) >> 1;
-                same &= same - 1u;
-                const double opx = ob(k, O_PX), ovx = ob(k, O_VX);
-                const bool take = (opx > c.px[a]) & (opx < bpx);
-                tmov_if(take, bpx, opx); tmov_if(take, bvx, ovx);
-            }
-            c.cruise[a] = bvx;
-        }
-        const int dl = (int)((fire >> 19) & 1u) - (int)((fire >> 18) & 1u);  // RIGHT +1, LEFT -1, only when it fires
-        c.ln[a] = min(max(c.ln[a] + dl, 1), 3);
-        c.acc[a] = tclamp(c.acc[a], -5.0, 5.0);
-        c.steer[a] = tclamp(c.steer[a], -30.0, 30.0);
-    }
-
-#endif
-    TPE_MARK(2);
     // ---- car updates in id order against last tick's leader (agent.py:79-165): a car subtracts the leader's velocity "as it is
     //      now" (agent.py:147-151) - its new value for the cars after it in id order, its old one for those before ----
     // Written as three passes over the cars (velocity and steering, angular velocity, position), each a straight line of A
@@ -437,7 +316,6 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         }
         c.b[a] = b;
     }
-    TPE_MARK(3);
     double lv = c.vx[0];  // the leader's velocity "as it is now" for the cars after it: its new value
 #pragma unroll
     for (int j = 1; j < A; ++j) tmov_if(L == j, lv, c.vx[j]);
@@ -449,7 +327,6 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         tset_if(!(c.steer[a] != 0.0), ang[a], 0.0);
         if (!CONT) c.vy[a] = ang[a];  // agent.py:144: velocity.y = angular_velocity (discrete update only)
     }
-    TPE_MARK(4);
 #pragma unroll
     for (int a = 0; a < A; ++a) {
         double lva = lv_old;
@@ -475,7 +352,6 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
     }
     const double lvdt = dmul(lv, dt);  // last tick's leader, this tick's velocity
 
-    TPE_MARK(5);
     // ---- leader / last election: stable sort of the cars by x, descending (highway_core.py:294-297).  In the reference it follows
     //      the obstacle updates, but it only reads the cars, which are final by now ----
     int lead = 0;
@@ -498,51 +374,12 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
     //      are in registers it is tested for a spawn / retire and against the cars' rects (an obstacle that is retired below is
     //      more than 14 m behind the last car, so testing it too cannot add an overlap in a consistent frame; the exact count
     //      walks the final list in any case) ----
-    TPE_MARK(6);
     const double thr = dsub(dsub(-2.375, plead), 2.0);
     const uint32_t newest_mask = (1u << h.newest[0]) | (1u << h.newest[1]) | (1u << h.newest[2]);  // 31 = retired: matches no slot
     bool want = false;
     for (int k = 0; k < (int)h.nobs; ++k) {
         const int lane = ob_lane(h, k);
         const double orx = ob(k, O_RX), iv = ob(k, O_IV);
-#if HW_TPE_OBS
-        // The nearest car ahead in the lane (first wins ties) WITHOUT a running minimum: a compare -> conditional move -> compare
-        // chain costs ~28 cycles per car on B200 (a DSETP delivers its predicate after ~20).  All candidate distances at once (inf for
-        // a car that is not ahead in this lane), all pairs compared side by side, the winner read off the predicates: car i wins iff
-        // it is valid and cand[i] <= cand[j] for every j > i and cand[j] > cand[i]... i.e. !(cand[j] <= cand[i]) for every j < i.
-        double cand[A];
-        bool w[A], any = false, sel = false;
-#pragma unroll
-        for (int j = 0; j < A; ++j) {
-            const double d = dsub(c.rx[j], orx);
-            w[j] = (c.ln[j] == lane) & (orx < c.rx[j]);
-            cand[j] = tpe_inf();
-            tmov_if(w[j], cand[j], d);
-            any = any | w[j];
-        }
-#pragma unroll
-        for (int i = 0; i < A; ++i) {
-#pragma unroll
-            for (int j = i + 1; j < A; ++j) {
-                const bool le = cand[i] <= cand[j];
-                w[i] = w[i] & le; w[j] = w[j] & !le;
-            }
-        }
-        // the winner's velocity: two short conditional-move chains over the halves of the cars, then one merge
-        constexpr int H = A / 2;
-        double bv = dcopy(c.vx[0]), bv2 = dcopy(c.vx[H]);
-        bool upper = w[H];
-#pragma unroll
-        for (int j = 1; j < H; ++j) tmov_if(w[j], bv, c.vx[j]);
-#pragma unroll
-        for (int j = H + 1; j < A; ++j) { tmov_if(w[j], bv2, c.vx[j]); upper = upper | w[j]; }
-        tmov_if(upper, bv, bv2);
-#pragma unroll
-        for (int j = 0; j < A; ++j) sel = sel | (w[j] & (c.vx[j] < iv));
-        double v = tclamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
-        tmov_if(any, v, iv);                 // else min(init_vx, that car's vx)
-        tmov_if(sel, v, bv);
-#else
         double bd = tpe_inf(), bv = iv;
 #pragma unroll
         for (int j = 0; j < A; ++j) {
@@ -553,7 +390,6 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
         double v = tclamp(iv, -20.0, 20.0);  // velocity.x = max(-20, min(init_vx, 20)) when nobody is ahead
         tmov_if(bd < tpe_inf(), v, iv);        // else min(init_vx, that car's vx)
         tmov_if(bv < iv, v, bv);
-#endif
         const double odt = dmul(v, dt);
         const double opx = dsub(dadd(ob(k, O_PX), odt), lvdt);
         const double orx2 = dadd(orx, odt);
@@ -563,7 +399,6 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
 #pragma unroll
         for (int a = 0; a < A; ++a) nohit = min(nohit, tpe_filter_word(pa[a], pb));
     }
-    TPE_MARK(7);
     h.ofresh = 0;  // every live obstacle has now written its rect
     if (inf_obs && want) {
         const TpeSlots r = tpe_spawn_retire(TpeSlots{h.nobs, h.olane, h.ofresh, h.newest[0], h.newest[1], h.newest[2], h.spawn_ctr, h.flags},
@@ -585,7 +420,6 @@ __device__ __forceinline__ uint32_t tpe_tick(MaHead &h, TpeCars<A> &c, const Tpe
     uint32_t hit = 0;
     if (nohit == 0u) hit = tpe_collide_exact<A>(h, c, ob);
     done |= hit;
-    TPE_MARK(8);
     return hit;
 }
 
@@ -704,11 +538,6 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
     uint32_t amask[A];
     double a0[A], a1[A];
     const uint64_t env_id = env_id0 + (uint64_t)i;
-#ifdef HW_TPE_PROF
-    TpeProf prof;
-    for (int j = 0; j < 12; ++j) prof.t[j] = 0;
-    prof.last = clock64();
-#endif
     if (live) {
         ma_load_head(h, S, i, n);
         // is_done persists until reset() (highway_core.py:239, :420): with HW_FLAG_NO_AUTORESET a car that finished in an earlier
@@ -747,7 +576,7 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
         for (int t = 0; t < C.ticks_per_step; ++t) {
             if (HW_TPE_SYNC == 1) __syncthreads();
             if (run) {
-                hit = tpe_tick<A, CONT, EXACT>(h, c, ob, K, C, dt, inf_obs, amask, a0, a1, seed, env_id, done TPE_PROF_PASS);
+                hit = tpe_tick<A, CONT, EXACT>(h, c, ob, K, C, dt, inf_obs, amask, a0, a1, seed, env_id, done);
                 if (done) run = false;  // highway_env.py:85-86: the step ends with the first tick that finishes a car
             }
         }
@@ -755,12 +584,11 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
 #else
     if (live) {
         for (int t = 0; t < C.ticks_per_step; ++t) {
-            hit = tpe_tick<A, CONT, EXACT>(h, c, ob, K, C, dt, inf_obs, amask, a0, a1, seed, env_id, done TPE_PROF_PASS);
+            hit = tpe_tick<A, CONT, EXACT>(h, c, ob, K, C, dt, inf_obs, amask, a0, a1, seed, env_id, done);
             if (done) break;  // highway_env.py:85-86: the step ends with the first tick that finishes a car
         }
     }
 #endif
-    TPE_MARK(9);   // barrier waits and the idle ticks of finished environments (the ticks themselves are marked inside)
     if (live) {
 
         // rewards of the step (Scenario.rewards of the last tick that ran, simple_base.py:65-80): -250 for a car that collided in it,
@@ -810,7 +638,6 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
             S.obst[(int64_t)k * n + i] = make_float4((float)ob(k, O_PX), (float)ob(k, O_RX), (float)ob(k, O_VX), (float)ob(k, O_IV));
     }
 
-    TPE_MARK(10);
     // observation rows: staged in the warp's (now free) shared region, kPass cars at a time, and streamed out 8 bytes per lane -
     // consecutive lanes write consecutive addresses of the environments' contiguous [A][4A+14] blocks
     constexpr int kPass = (kTpeWarpDoubles / 32) / D2 < A ? (kTpeWarpDoubles / 32) / D2 : A;  // cars per pass that fit the region
@@ -846,13 +673,6 @@ ma_tpe_step_kernel(MaPtrs S, const void *__restrict__ actions, float *__restrict
         }
     }
 
-    TPE_MARK(11);
-#ifdef HW_TPE_PROF
-    if (lane_id == 0) {
-        for (int j = 0; j < 12; ++j) atomicAdd(&g_tpe_prof[j], (unsigned long long)prof.t[j]);
-        atomicAdd(&g_tpe_prof[12], 1ull);
-    }
-#endif
     if (stats) {
         if (__any_sync(0xffffffffu, acc[0] != 0)) {
 #pragma unroll
@@ -908,14 +728,3 @@ int ma_tpe_launch_step(const HwMaState *st, const void *actions, const HwMaOut *
 
 }  // namespace hw
 
-#ifdef HW_TPE_PROF
-extern "C" int hw_debug_tpe_prof(unsigned long long *host16, int reset)
-{
-    cudaError_t e = cudaMemcpyFromSymbol(host16, hw::g_tpe_prof, sizeof(hw::g_tpe_prof));
-    if (e == cudaSuccess && reset) {
-        unsigned long long z[16] = {0};
-        e = cudaMemcpyToSymbol(hw::g_tpe_prof, z, sizeof(z));
-    }
-    return (int)e;
-}
-#endif

@@ -374,14 +374,9 @@ __device__ __forceinline__ void sa_tick_later(SaEnv &e, int &lane, int &ncol, in
     }
     {
         double v = dadd(e.vx, dmul(e.acc, dt));
-#if HW_CLAMP_PAR
         const bool over = 20.0 < v, under = !(v > 0.0);  // max(0.0, v) is v only when v > 0; both tests on the value before either move
         dset_if(over, v, 20.0);
         dset_if(under, v, 0.0);
-#else
-        dset_if(20.0 < v, v, 20.0);
-        dset_if(!(v > 0.0), v, 0.0);  // max(0.0, v) is v only when v > 0
-#endif
         e.vx = v;
     }
     const double vdt = dmul(e.vx, dt);
