@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <string.h>
 #include "philox.h"
+#include "tan_small.h"
 
 #define HW_PI 3.14159265358979323846
 static const double DEG2RAD = HW_PI / 180.0;
@@ -150,7 +151,7 @@ static void ma_tick(ma_env *e, double dt, int timeout_tick, int cont, int inf_ob
             }
         }
         double ang = 0.0;
-        if (c->steer != 0.0) ang = c->vx / (4.0 / tan(c->steer * DEG2RAD));
+        if (c->steer != 0.0) ang = c->vx / (4.0 / hw_tan(c->steer * DEG2RAD));
         if (!cont) c->vy = ang; /* agent.py:144: velocity.y = angular_velocity (discrete only) */
         c->px = c->px + c->vx * dt;
         c->py = c->py + c->vy * dt;

@@ -25,7 +25,7 @@ LANE_C = (1.25, 3.75, 6.25)
 
 def build(force=False):
     """compile the C restatement with gcc (seconds)"""
-    srcs = [os.path.join(_HERE, f) for f in ("sa_oracle.c", "ma_oracle.c", "philox.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("sa_oracle.c", "ma_oracle.c", "philox.h", "tan_small.h", "Makefile")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
         return _SO
@@ -45,6 +45,12 @@ def lib():
         _lib.hw_oracle_sa_reset.restype = C.c_int
         _lib.hw_oracle_sa_observe.restype = C.c_int
     return _lib
+
+
+def set_tan(poly):
+    """which tangent the restatement evaluates: False = libm's (the reference's, default), True = the kernels' polynomial
+    (diagnosis of soak mismatches only, see tan_small.h)"""
+    lib().hw_oracle_set_tan(1 if poly else 0)
 
 
 def sim_params(real_time=False):

@@ -28,6 +28,10 @@
 #include <stdint.h>
 #include <string.h>
 #include "philox.h"
+#include "tan_small.h"
+
+int hw_oracle_tan_poly = 0; /* 0: libm tan (the reference's); 1: the kernels' polynomial, for diagnosing soak mismatches (tan_small.h) */
+void hw_oracle_set_tan(int poly) { hw_oracle_tan_poly = poly; }
 
 #define HW_PI 3.14159265358979323846
 static const double DEG2RAD = HW_PI / 180.0; /* math.radians: x * (pi/180) */
@@ -158,7 +162,7 @@ static double sa_tick(sa_env *e, const hw_sim_params *P, int cont, int inf_obs, 
     }
     double ang = 0.0;
     if (e->steer != 0.0) {
-        double radius = 4.0 / tan(e->steer * DEG2RAD);
+        double radius = 4.0 / hw_tan(e->steer * DEG2RAD);
         ang = e->vx / radius;
     }
     e->px = e->px + e->vx * dt; /* position += velocity*dt; velocity.y == 0 in the single-agent sim */

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import ma_oracle as mo
+from oracle import ma_oracle as mo, oracle as orc
 from helpers import MA_STATE_FIELDS, bits_equal, f32, load_golden, ma_state_from_golden
 
 pytestmark = pytest.mark.gpu
@@ -255,3 +255,37 @@ def test_extension_beyond_five_cars_matches_its_cpu_specification(A, continuous)
     for f in MA_STATE_FIELDS + ("ep_len", "ep_ret"):
         assert np.array_equal(getattr(got, f), getattr(st, f)), f
     assert nd > n // 4 and int(env.diagnostics().max()) == 0
+
+
+def test_the_only_difference_from_the_libm_oracle_is_the_declared_tangent_ulp():
+    """DESIGN.md deviation 3, pinned on the one early event a 4.9e8-env-step soak found (profiles/r4k_soak_diagnose.json: env 4283, step 6,
+    car 2, column 9 - a relative lateral offset - one float32 ulp): the kernels' tangent polynomial is within 1 ulp(fp64) of libm's tan,
+    and about once per 10^9 car-ticks that ulp reaches a float32 the step returns.  Against the oracle evaluating the SAME polynomial
+    (oracle/tan_small.h) every value is bit-identical; against the libm oracle the differences are isolated observation floats within
+    2 float32 ulps and never a discrete output."""
+    n, A, steps, seed0 = 4352, 5, 8, 1000
+    for kernel in ("thread", "group"):
+        counts = {}
+        for poly in (False, True):
+            orc.set_tan(poly)
+            try:
+                env = _env(n, A, seed=22 + seed0, env_id0=3, exact_steering=True, kernel=kernel)
+                st = mo.MaState(n, A); mo.ma_reset(st)
+                rng = np.random.RandomState(8 + seed0)
+                bad, worst = 0, 0
+                for t in range(steps):
+                    act = rng.randint(0, 4, (65536, A)).astype(np.int32)[:n]   # the soak job's action stream, first n environments
+                    obs, rew, done, _ = env.step(torch.from_numpy(np.ascontiguousarray(act)).cuda())
+                    want = mo.ma_step(st, act, seed=22 + seed0, env_id0=3, quantise=True, nthreads=8)
+                    assert np.array_equal(done.cpu().numpy(), want["done"])
+                    assert bits_equal(rew.cpu().numpy(), f32(want["rew"]))
+                    o, w = obs.cpu().numpy(), f32(want["obs"])
+                    neq = o.view(np.uint32) != w.view(np.uint32)
+                    bad += int(neq.sum())
+                    if neq.any():
+                        worst = max(worst, int(np.abs(o[neq].view(np.int32).astype(np.int64) - w[neq].view(np.int32).astype(np.int64)).max()))
+                counts[poly] = (bad, worst)
+            finally:
+                orc.set_tan(False)
+        assert counts[True] == (0, 0), "kernel %s differs from the oracle with its own tangent: %r" % (kernel, counts[True])
+        assert counts[False][0] <= 4 and counts[False][1] <= 2, counts[False]
