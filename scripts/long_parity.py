@@ -37,27 +37,28 @@ def _compare(counts, obs, want_obs, done, want_done, rew=None, want_rew=None):
         counts["rew"] += int((rew.cpu().numpy().view(np.uint32) != want_rew.astype(np.float32).view(np.uint32)).sum())
 
 
-def _run_sa(n, steps, cont, poly):
+def _run_sa(n, steps, cont, poly, real_time=False, inf_obs=True):
     orc.set_tan(poly)
-    env = HighwayVecEnv(n, continuous=cont, seed=21 + SEED0, env_id0=5, exact_steering=True)
+    env = HighwayVecEnv(n, continuous=cont, seed=21 + SEED0, env_id0=5, exact_steering=True, real_time=real_time, inf_obs=inf_obs)
     st = orc.SaState(n); orc.sa_reset(st)
     rng = np.random.RandomState(7 + SEED0)
     c = dict(obs=0, done=0, rew=0, max_ulps=0, kernels=0)
     for t in range(steps):
         act = rng.uniform(-1, 1, (n, 2)).astype(np.float32) if cont else rng.randint(0, 4, n).astype(np.int32)
         obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
-        want = orc.sa_step(st, act, continuous=cont, seed=21 + SEED0, env_id0=5, quantise=True, nthreads=16)
+        want = orc.sa_step(st, act, continuous=cont, seed=21 + SEED0, env_id0=5, quantise=True, nthreads=16, real_time=real_time, inf_obs=inf_obs)
         _compare(c, obs, want["obs"], done, want["done"], rew, want["rew"])
     orc.set_tan(False)
     return c, dict(episodes=int(env.episode_statistics()["episodes"]))
 
 
-def _run_ma(n, steps, cont, A, uniform, poly):
+def _run_ma(n, steps, cont, A, uniform, poly, real_time=False, inf_obs=True, shared_reward=False):
     ext = A > 5
     orc.set_tan(poly)
-    env = HighwayMAVecEnv(n, num_agents=A, continuous=cont, seed=22 + SEED0, env_id0=3, exact_steering=True, kernel="thread", extended_agents=ext)
-    env2 = HighwayMAVecEnv(n, num_agents=A, continuous=cont, seed=22 + SEED0, env_id0=3, exact_steering=True, kernel="thread" if ext else "group",
-                           extended_agents=ext)
+    kw = dict(num_agents=A, continuous=cont, seed=22 + SEED0, env_id0=3, exact_steering=True, extended_agents=ext, shared_reward=shared_reward,
+              world_config=dict(real_time=real_time, inf_obs=inf_obs))
+    env = HighwayMAVecEnv(n, kernel="thread", **kw)
+    env2 = HighwayMAVecEnv(n, kernel="thread" if ext else "group", **kw)
     st = mo.MaState(n, A); mo.ma_reset(st)
     rng = np.random.RandomState(8 + SEED0)
     c = dict(obs=0, done=0, rew=0, max_ulps=0, kernels=0)
@@ -71,8 +72,9 @@ def _run_ma(n, steps, cont, A, uniform, poly):
         obs, rew, done, _ = env.step(a)
         obs2, rew2, done2, _ = env2.step(a)
         c["kernels"] += int((obs != obs2).sum()) + int((done != done2).sum())
-        want = mo.ma_step(st, act, continuous=cont, seed=22 + SEED0, env_id0=3, quantise=True, nthreads=16)
-        _compare(c, obs, want["obs"], done, want["done"])
+        want = mo.ma_step(st, act, continuous=cont, seed=22 + SEED0, env_id0=3, quantise=True, nthreads=16, real_time=real_time, inf_obs=inf_obs,
+                          shared_reward=shared_reward)
+        _compare(c, obs, want["obs"], done, want["done"], rew, want["rew"])
     orc.set_tan(False)
     return c, dict(max_live_obstacles=int(st.nobs.max()), overflow=int(env.diagnostics().max()), episodes=int(env.episode_statistics()["episodes"]))
 
@@ -99,23 +101,27 @@ def _job(label, runner, record):
     return unexplained
 
 
-def soak_sa(n, steps, cont):
+def soak_sa(n, steps, cont, **modes):
     steps *= SCALE
-    return _job("SA cont=%d  %d envs x %d steps" % (cont, n, steps), lambda poly: _run_sa(n, steps, cont, poly),
-                dict(env="sa", continuous=bool(cont), envs=n, steps=steps))
+    return _job("SA cont=%d %s %d envs x %d steps" % (cont, modes or "", n, steps), lambda poly: _run_sa(n, steps, cont, poly, **modes),
+                dict(env="sa", continuous=bool(cont), envs=n, steps=steps, **modes))
 
 
-def soak_ma(n, steps, cont, A=5, uniform=False):
+def soak_ma(n, steps, cont, A=5, uniform=False, **modes):
     steps *= SCALE
-    return _job("MA cont=%d A=%d  %d envs x %d steps" % (cont, A, n, steps), lambda poly: _run_ma(n, steps, cont, A, uniform, poly),
-                dict(env="ma", agents=A, continuous=bool(cont), uniform_actions=bool(uniform), envs=n, steps=steps))
+    return _job("MA cont=%d A=%d %s %d envs x %d steps" % (cont, A, modes or "", n, steps), lambda poly: _run_ma(n, steps, cont, A, uniform, poly, **modes),
+                dict(env="ma", agents=A, continuous=bool(cont), uniform_actions=bool(uniform), envs=n, steps=steps, **modes))
 
 
 if __name__ == "__main__":
     total = (soak_sa(65536, 600, False) + soak_sa(65536, 300, True) + soak_ma(24576, 500, False) + soak_ma(24576, 300, True)
              + soak_ma(9999, 300, False, A=3) + soak_ma(65536, 250, False, uniform=True) + soak_ma(65536, 150, True, uniform=True)
              + soak_ma(20011, 200, False, A=1) + soak_ma(20011, 200, True, A=2) + soak_ma(20011, 200, False, A=4)
-             + soak_ma(8191, 200, False, A=8) + soak_ma(8191, 150, True, A=6))
+             + soak_ma(8191, 200, False, A=8) + soak_ma(8191, 150, True, A=6)
+             # the other modes of the path: 60 Hz clock (15 ticks per step), no respawns, shared reward
+             + soak_sa(32768, 150, False, real_time=True) + soak_sa(32768, 150, True, inf_obs=False)
+             + soak_ma(16384, 120, False, uniform=True, shared_reward=True) + soak_ma(16384, 100, False, uniform=True, real_time=True)
+             + soak_ma(16384, 100, True, A=3, uniform=True, inf_obs=False))
     steps = sum(r["envs"] * r["steps"] for r in RESULTS)
     explained = sum(r["mismatching_values"] for r in RESULTS if r.get("explained_by_the_tangent_deviation"))
     print("long parity:", "OK" if total == 0 else "FAILED (%d unexplained)" % total, "- %.2e env-steps compared, %d values explained by the tangent deviation"
