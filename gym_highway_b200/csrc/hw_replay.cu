@@ -127,6 +127,7 @@ moments_slab_kernel(const float *__restrict__ x, const long long n, const int C,
     if (c >= C) return;
     const long long r0 = slab * kMomentRows, r1 = r0 + kMomentRows < n ? r0 + kMomentRows : n;
     // four interleaved accumulators (rows r0 + 4j + i) so that four loads are in flight per thread; combined in a fixed order
+    // (eight in flight measured slower: 37 vs 21.5 us for a 45 MB block)
     double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};
     long long r = r0;
     for (; r + 4 <= r1; r += 4) {
@@ -150,8 +151,19 @@ moments_finish_kernel(const double *__restrict__ partial, const long long slabs,
     __shared__ double part[32][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0;
-    if (c < 2 * C)
-        for (long long k = threadIdx.y; k < slabs; k += 32) s += partial[k * 2 * C + c];
+    if (c < 2 * C) {
+        // eight loads in flight, added in slab order (the same sum as a plain loop; issued one by one the loop was a chain of 32
+        // dependent L2 round trips on 11 blocks: 10 us)
+        long long k = threadIdx.y;
+        for (; k + 7 * 32 < slabs; k += 8 * 32) {
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = partial[(k + 32 * i) * 2 * C + c];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += v[i];
+        }
+        for (; k < slabs; k += 32) s += partial[k * 2 * C + c];
+    }
     part[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < 2 * C) {
