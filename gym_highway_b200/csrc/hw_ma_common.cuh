@@ -108,10 +108,12 @@ __device__ __forceinline__ void ma_norm_n(const double (&raw)[N], float (&out)[N
     for (int i = 0; i < N; ++i) x[i] = dsub((double)v[i], ma_bnd_lo(B[i]));
 #pragma unroll
     for (int i = 0; i < N; ++i) q0[i] = dmul(x[i], 1.0 / (ma_bnd_hi(B[i]) - ma_bnd_lo(B[i])));
+    // spans of 8 and 16 (the lateral quantities) divide exactly by the multiplication above: no correction step
 #pragma unroll
-    for (int i = 0; i < N; ++i) e[i] = __fma_rn(-q0[i], ma_bnd_hi(B[i]) - ma_bnd_lo(B[i]), x[i]);
+    for (int i = 0; i < N; ++i) e[i] = (B[i] == 3 || B[i] == 5) ? 0.0 : __fma_rn(-q0[i], ma_bnd_hi(B[i]) - ma_bnd_lo(B[i]), x[i]);
 #pragma unroll
-    for (int i = 0; i < N; ++i) out[i] = (float)__fma_rn(e[i], 1.0 / (ma_bnd_hi(B[i]) - ma_bnd_lo(B[i])), q0[i]);
+    for (int i = 0; i < N; ++i)
+        out[i] = (float)((B[i] == 3 || B[i] == 5) ? q0[i] : __fma_rn(e[i], 1.0 / (ma_bnd_hi(B[i]) - ma_bnd_lo(B[i])), q0[i]));
 }
 
 
