@@ -200,6 +200,9 @@ def timed_steps(env, acts, steps, warmup, flush_buf, world, dev, sampler=None):
     ring = acts.shape[0]
     if hasattr(env, "rollout_random"):
         env.rollout_random(150, action_ctr0=0)  # decorrelate the batch: episodes at different phases
+    else:
+        for w in range(40):                      # no in-kernel random roll-out for the multi-agent env: ordinary steps do the same
+            env.step_async(acts[w % ring]); env.step_wait()
     for w in range(max(warmup, 3)):
         env.step_async(acts[w % ring]); env.step_wait()
     torch.cuda.synchronize(dev)
@@ -244,10 +247,7 @@ def side_measure(kind, continuous, n, dev, rank, args, steps=100, warmup=5, agen
     bps = SA_BYTES_PER_STEP[continuous] if kind == "sa" else ma_bytes_per_step(A, 16)
     flush = n * bps < 2 * L2_BYTES
     fb = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if flush else None
-    if kind == "ma":  # no in-kernel random roll-out for the multi-agent env: decorrelate with ordinary steps
-        for w in range(40):
-            env.step_async(acts[w % acts.shape[0]]); env.step_wait()
-    ms, wall = timed_steps(env, acts, steps, warmup, fb, 1, dev)
+    ms, wall = timed_steps(env, acts, steps, warmup, fb, 1, dev)  # decorrelates the batch first
     peak = measured_peak()[0]
     t = float(ms.mean()) * 1e-3
     out = {"envs": n, "avg_launch_us": t * 1e6, "min_launch_us": float(ms.min()) * 1e3, "env_steps_per_s": n / t,
